@@ -1,0 +1,162 @@
+// Row gather (index_select along dim 0) and the last-dim segment reduce
+// (index_select / index_add_ along dim 1 of a [B, L] matrix).
+#include <climits>
+
+#include "common.cuh"
+
+namespace gno {
+
+template <typename V>
+__global__ void __launch_bounds__(256)
+    gather_rows_kernel(const V* __restrict__ x, const int64_t* __restrict__ index,
+                       V* __restrict__ out, int64_t n_index, int64_t vpr, int64_t x_rows) {
+  const int64_t total = n_index * vpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i / vpr, j = i - k * vpr;
+    int64_t r = index[k];
+    r = r < 0 ? 0 : (r >= x_rows ? x_rows - 1 : r);  // clamp: never read outside x
+    out[i] = __ldg(x + r * vpr + j);
+  }
+}
+
+// out[b, i] = reduce_{k in row i} x[b, gidx[k]].  One CTA per source row b:
+// the row is staged in shared memory once (coalesced), then every thread
+// walks the sorted edges of its destination columns.  RED as gno_reduce.
+template <typename T, int RED, bool STAGE>
+__global__ void __launch_bounds__(256)
+    lastdim_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ gidx,
+                   const int32_t* __restrict__ eid, const T* __restrict__ x, int64_t L,
+                   int64_t ldx, T* __restrict__ out, int64_t ldo, int64_t* __restrict__ arg,
+                   int64_t arg_fill, int64_t N, int mean, int accumulate) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* srow = reinterpret_cast<T*>(smem_raw);
+  const int64_t b = blockIdx.x;
+  const T* xrow = x + b * ldx;
+  if (STAGE) {
+    for (int64_t j = threadIdx.x; j < L; j += blockDim.x) srow[j] = xrow[j];
+    __syncthreads();
+  }
+  const T* src = STAGE ? srow : xrow;
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+    const int64_t kb = rowptr[i], ke = rowptr[i + 1];
+    float a;
+    if (RED == GNO_SUM) a = 0.f;
+    else if (RED == GNO_MUL) a = 1.f;
+    else if (RED == GNO_MAX) a = DType<T>::lowest();
+    else a = DType<T>::highest();
+    int64_t e = -1;
+    for (int64_t k = kb; k < ke; ++k) {
+      const int64_t g = gidx ? (int64_t)__ldg(gidx + k) : k;
+      const float f = DType<T>::to_f(src[g]);
+      if (RED == GNO_SUM) a += f;
+      else if (RED == GNO_MUL) a *= f;
+      else if (RED == GNO_MAX) { if (f > a) { a = f; e = k; } }
+      else { if (f < a) { a = f; e = k; } }
+    }
+    T* op = out + b * ldo + i;
+    if (RED == GNO_SUM) {
+      if (mean) a = a / (float)imax64(ke - kb, 1);
+      if (accumulate) a += DType<T>::to_f(*op);
+    } else if (RED == GNO_MUL) {
+      if (accumulate) a *= DType<T>::to_f(*op);
+    } else {
+      if (e < 0) a = 0.f;
+      if (arg) arg[b * N + i] = (e < 0) ? arg_fill : (eid ? (int64_t)__ldg(eid + e) : e);
+    }
+    *op = DType<T>::from_f(a);
+  }
+}
+
+template <typename T, int RED>
+static int launch_lastdim(const gno_csr* g, const void* x, int64_t B, int64_t L, int64_t ldx,
+                          void* out, int64_t ldo, int64_t* arg, int64_t arg_fill, int mean,
+                          int accumulate, cudaStream_t s) {
+  const size_t bytes = (size_t)L * sizeof(T);
+  const bool stage = bytes <= 200 * 1024;
+  if (stage) {
+    auto k = lastdim_kernel<T, RED, true>;
+    if (bytes > 48 * 1024)
+      GNO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    k<<<(unsigned)B, 256, bytes, s>>>(g->rowptr, g->gidx, g->eid, (const T*)x, L, ldx, (T*)out, ldo,
+                                       arg, arg_fill, g->N, mean, accumulate);
+  } else {
+    lastdim_kernel<T, RED, false><<<(unsigned)B, 256, 0, s>>>(
+        g->rowptr, g->gidx, g->eid, (const T*)x, L, ldx, (T*)out, ldo, arg, arg_fill, g->N, mean,
+        accumulate);
+  }
+  GNO_LAUNCHED("lastdim_kernel");
+  return GNO_OK;
+}
+
+template <typename T>
+static int dispatch_lastdim(int reduce, const gno_csr* g, const void* x, int64_t B, int64_t L,
+                            int64_t ldx, void* out, int64_t ldo, int64_t* arg, int64_t arg_fill,
+                            int accumulate, cudaStream_t s) {
+  switch (reduce) {
+    case GNO_SUM: return launch_lastdim<T, GNO_SUM>(g, x, B, L, ldx, out, ldo, arg, arg_fill, 0, accumulate, s);
+    case GNO_MEAN: return launch_lastdim<T, GNO_SUM>(g, x, B, L, ldx, out, ldo, arg, arg_fill, 1, accumulate, s);
+    case GNO_MUL: return launch_lastdim<T, GNO_MUL>(g, x, B, L, ldx, out, ldo, arg, arg_fill, 0, accumulate, s);
+    case GNO_MIN: return launch_lastdim<T, GNO_MIN>(g, x, B, L, ldx, out, ldo, arg, arg_fill, 0, accumulate, s);
+    case GNO_MAX: return launch_lastdim<T, GNO_MAX>(g, x, B, L, ldx, out, ldo, arg, arg_fill, 0, accumulate, s);
+  }
+  return fail(GNO_ERR_INVALID, "gno_segment_reduce_lastdim: unknown reduce %d", reduce);
+}
+
+}  // namespace gno
+
+using namespace gno;
+
+extern "C" {
+
+int gno_gather_rows(const void* x, int64_t x_rows, int64_t row_bytes, const int64_t* index,
+                    int64_t n_index, void* out, gno_stream_t stream) {
+  if (n_index == 0 || row_bytes == 0) return GNO_OK;
+  GNO_CHECK_ARG(x && index && out && x_rows > 0 && n_index > 0 && row_bytes > 0,
+                "gno_gather_rows: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const uintptr_t a = (uintptr_t)x | (uintptr_t)out | (uintptr_t)row_bytes;
+  auto grid = [](int64_t n) {
+    int64_t b = ceil_div(n, 256);
+    return (unsigned)(b > (int64_t)kNumSMs * 32 ? (int64_t)kNumSMs * 32 : b);
+  };
+  if (a % 16 == 0) {
+    const int64_t vpr = row_bytes / 16;
+    gather_rows_kernel<uint4><<<grid(n_index * vpr), 256, 0, s>>>((const uint4*)x, index, (uint4*)out, n_index, vpr, x_rows);
+  } else if (a % 8 == 0) {
+    const int64_t vpr = row_bytes / 8;
+    gather_rows_kernel<uint2><<<grid(n_index * vpr), 256, 0, s>>>((const uint2*)x, index, (uint2*)out, n_index, vpr, x_rows);
+  } else if (a % 4 == 0) {
+    const int64_t vpr = row_bytes / 4;
+    gather_rows_kernel<uint32_t><<<grid(n_index * vpr), 256, 0, s>>>((const uint32_t*)x, index, (uint32_t*)out, n_index, vpr, x_rows);
+  } else if (a % 2 == 0) {
+    const int64_t vpr = row_bytes / 2;
+    gather_rows_kernel<uint16_t><<<grid(n_index * vpr), 256, 0, s>>>((const uint16_t*)x, index, (uint16_t*)out, n_index, vpr, x_rows);
+  } else {
+    gather_rows_kernel<uint8_t><<<grid(n_index * row_bytes), 256, 0, s>>>((const uint8_t*)x, index, (uint8_t*)out, n_index, row_bytes, x_rows);
+  }
+  GNO_LAUNCHED("gather_rows_kernel");
+  return GNO_OK;
+}
+
+int gno_segment_reduce_lastdim(const gno_csr* g, const void* x, int64_t B, int64_t L, int64_t ldx,
+                               void* out, int64_t ldo, int64_t* arg, int64_t arg_fill, int dtype,
+                               int reduce, int accumulate, gno_stream_t stream) {
+  GNO_CHECK_ARG(g != nullptr, "gno_segment_reduce_lastdim: graph is NULL");
+  GNO_CHECK_ARG(B >= 0 && L >= 0 && ldx >= L && ldo >= g->N, "gno_segment_reduce_lastdim: bad sizes");
+  GNO_CHECK_ARG(!accumulate || reduce == GNO_SUM || reduce == GNO_MUL,
+                "gno_segment_reduce_lastdim: accumulate only for SUM/MUL");
+  GNO_CHECK_ARG(arg == nullptr || reduce == GNO_MIN || reduce == GNO_MAX,
+                "gno_segment_reduce_lastdim: arg output only for MIN/MAX");
+  if (B == 0 || g->N == 0) return GNO_OK;
+  GNO_CHECK_ARG(g->rowptr && out && (x || g->E == 0), "gno_segment_reduce_lastdim: NULL buffer");
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case GNO_F32: return dispatch_lastdim<float>(reduce, g, x, B, L, ldx, out, ldo, arg, arg_fill, accumulate, s);
+    case GNO_F16: return dispatch_lastdim<__half>(reduce, g, x, B, L, ldx, out, ldo, arg, arg_fill, accumulate, s);
+    case GNO_BF16: return dispatch_lastdim<__nv_bfloat16>(reduce, g, x, B, L, ldx, out, ldo, arg, arg_fill, accumulate, s);
+  }
+  return fail(GNO_ERR_INVALID, "gno_segment_reduce_lastdim: unknown dtype %d", dtype);
+}
+
+}  // extern "C"

@@ -1,0 +1,468 @@
+"""Operator layer: torch tensors in, C-ABI calls out (include/gno_b200.h).
+
+Semantics follow torch-scatter 2.0.9 / torch-sparse 0.6.12 as the reference
+scripts call them (op_bm_scripts/benchmark_scatter_*.py:15-19,
+benchmark_sparse_coalesce.py:35-37) and the native torch ops they time
+(benchmark_native_index_add_.py:13-16, benchmark_native_sort.py:28-30,
+benchmark_sparse_spmm.py:12-14).  Everything runs on the CUDA library; CPU
+tensors are rejected (there is no fallback).
+"""
+import collections
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (GNO_BF16, GNO_F16, GNO_F32, GNO_MAX, GNO_MEAN, GNO_MIN, GNO_MUL, GNO_SUM,
+                   REDUCE_IDS, GnoError, check, lib)
+from .plan import (DEFAULT_SPLIT_LEN, CSRPlan, _ptr, _stream, _workspace, build_plan, plan_cache,
+                   plan_from_rowptr)
+
+_DTYPES = {torch.float32: GNO_F32, torch.float16: GNO_F16, torch.bfloat16: GNO_BF16}
+
+
+def _dtype_id(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise GnoError(f"gno_b200: unsupported dtype {t.dtype} (float32/float16/bfloat16 only)")
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise GnoError("gno_b200 has no CPU path: tensors must live on a CUDA device")
+
+
+def _reduce_id(reduce):
+    try:
+        return REDUCE_IDS[reduce]
+    except KeyError:
+        raise ValueError(f"unknown reduce '{reduce}'")
+
+
+_memo_store = collections.OrderedDict()
+
+
+def _memo(kind, t, extra, builder, capacity=8):
+    """Small LRU keyed on a tensor's identity/version (keeps the tensor alive)."""
+    key = (kind, t.data_ptr(), t._version, t.numel(), str(t.device)) + tuple(extra)
+    hit = _memo_store.get(key)
+    if hit is not None:
+        _memo_store.move_to_end(key)
+        return hit[0]
+    val = builder()
+    _memo_store[key] = (val, t)
+    while len(_memo_store) > capacity:
+        _memo_store.popitem(last=False)
+    return val
+
+
+def clear_caches():
+    plan_cache.clear()
+    _memo_store.clear()
+
+
+# ------------------------------------------------------------ segment reduce --
+def segment_reduce(plan, x, reduce, *, gidx=None, eid=None, weights=None, out=None,
+                   accumulate=False, want_arg=False, arg_fill=None):
+    """out[i, :] = reduce_{k in row i} weights[k] * x[gidx[k], :]   (x is 2-D).
+
+    gidx/eid: int32 [E] tensors or None (identity).  Returns out or (out, arg).
+    """
+    _need_cuda(x, gidx, eid, weights, out)
+    if x.dim() != 2:
+        raise ValueError("segment_reduce expects a 2-D x")
+    if x.stride(1) != 1 and x.size(1) > 1:
+        x = x.contiguous()
+    red = _reduce_id(reduce)
+    dt = _dtype_id(x)
+    N, F = plan.N, x.size(1)
+    dev = x.device
+    if out is None:
+        out = torch.empty((N, F), dtype=x.dtype, device=dev)
+    elif out.dtype != x.dtype or out.dim() != 2 or out.size(0) != N or out.size(1) != F or \
+            (out.stride(1) != 1 and F > 1):
+        raise ValueError("segment_reduce: bad out tensor")
+    arg = None
+    if want_arg:
+        arg = torch.empty((N, F), dtype=torch.int64, device=dev)
+    if arg_fill is None:
+        arg_fill = plan.E
+    if weights is not None:
+        weights = weights.to(x.dtype).contiguous()
+    csr = plan.csr(gidx, eid if want_arg else None)
+    nbytes = ctypes.c_size_t()
+    check(lib.gno_segment_reduce_workspace(ctypes.byref(csr), F, dt, red, 1 if want_arg else 0,
+                                           ctypes.byref(nbytes)))
+    ws = _workspace(nbytes.value, dev) if nbytes.value else None
+    ldx = x.stride(0) if x.size(0) > 1 else max(F, 1)
+    ldo = out.stride(0) if N > 1 else max(F, 1)
+    with torch.cuda.device(dev):
+        check(lib.gno_segment_reduce(ctypes.byref(csr), _ptr(x), x.size(0), ldx, _ptr(weights),
+                                     _ptr(out), ldo, _ptr(arg), int(arg_fill), F, dt, red,
+                                     1 if accumulate else 0, _ptr(ws), nbytes.value, _stream(dev)))
+    return (out, arg) if want_arg else out
+
+
+def _segment_reduce_lastdim(plan, x2d, reduce, gidx, eid, out2d, accumulate, want_arg, arg_fill):
+    red = _reduce_id(reduce)
+    dt = _dtype_id(x2d)
+    dev = x2d.device
+    B, L = x2d.shape
+    arg = torch.empty((B, plan.N), dtype=torch.int64, device=dev) if want_arg else None
+    csr = plan.csr(gidx, eid if want_arg else None)
+    with torch.cuda.device(dev):
+        check(lib.gno_segment_reduce_lastdim(ctypes.byref(csr), _ptr(x2d), B, L, x2d.stride(0) if B > 1 else L,
+                                             _ptr(out2d), out2d.stride(0) if B > 1 else plan.N,
+                                             _ptr(arg), int(arg_fill), dt, red,
+                                             1 if accumulate else 0, _stream(dev)))
+    return arg
+
+
+# -------------------------------------------------------------------- scatter --
+def _index_as_1d(index, src, dim):
+    """Return the 1-D index if `index` is 1-D or a stride-0 broadcast of one, else None."""
+    if index.dim() == 1:
+        return index if (src.dim() == 1 or index.numel() == src.size(dim)) else None
+    if index.dim() != src.dim():
+        return None
+    for d in range(index.dim()):
+        if d != dim and index.size(d) > 1 and index.stride(d) != 0:
+            return None
+    if index.size(dim) != src.size(dim):
+        return None
+    return index.as_strided((index.size(dim),), (index.stride(dim),), index.storage_offset())
+
+
+def scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum", return_arg=False):
+    """torch_scatter.scatter semantics; returns out or (out, arg) for min/max with return_arg."""
+    _need_cuda(src, index, out)
+    red = _reduce_id(reduce)
+    if index.dtype != torch.int64:
+        raise ValueError("index must be int64")
+    if dim < 0:
+        dim += src.dim()
+    if dim < 0 or dim >= src.dim():
+        raise IndexError("dim out of range")
+    want_arg = return_arg and red in (GNO_MIN, GNO_MAX)
+    if out is not None and red not in (GNO_SUM, GNO_MUL):
+        raise NotImplementedError("gno_b200: out= is supported for sum/mul only")
+
+    idx1d = _index_as_1d(index, src, dim)
+    if idx1d is None:
+        if index.dim() != src.dim():
+            raise ValueError("index must be 1-D or have as many dims as src")
+        if tuple(index.shape) != tuple(src.shape):
+            if any(i > s for i, s in zip(index.shape, src.shape)):
+                raise ValueError("index is larger than src")
+            src = src[tuple(slice(0, s) for s in index.shape)]
+    if dim_size is not None:
+        N = int(dim_size)
+    elif out is not None:
+        N = out.size(dim)
+    else:
+        N = int(index.max()) + 1 if index.numel() > 0 else 0  # host sync, as upstream
+
+    src = src.contiguous()
+    shape = list(src.shape)
+    E = shape[dim]
+    B = 1
+    for s in shape[:dim]:
+        B *= s
+    K = 1
+    for s in shape[dim + 1:]:
+        K *= s
+    out_shape = shape[:dim] + [N] + shape[dim + 1:]
+    accumulate = out is not None
+    if accumulate:
+        if list(out.shape) != out_shape or not out.is_contiguous() or out.dtype != src.dtype:
+            raise ValueError("out has the wrong shape/dtype or is not contiguous")
+    else:
+        out = torch.empty(out_shape, dtype=src.dtype, device=src.device)
+    arg = None
+
+    if idx1d is not None:
+        plan = plan_cache.get(idx1d.contiguous() if not idx1d.is_contiguous() else idx1d, N)
+        if K == 1 and B > 1:
+            arg2 = _segment_reduce_lastdim(plan, src.view(B, E), reduce, plan.perm, plan.perm,
+                                           out.view(B, N), accumulate, want_arg, E)
+            if want_arg:
+                arg = arg2.view(out_shape)
+        else:
+            s3, o3 = src.view(B, E, K), out.view(B, N, K)
+            args = []
+            for b in range(B):
+                r = segment_reduce(plan, s3[b], reduce, gidx=plan.perm, eid=plan.perm, out=o3[b],
+                                   accumulate=accumulate, want_arg=want_arg, arg_fill=E)
+                if want_arg:
+                    args.append(r[1])
+            if want_arg:
+                arg = (args[0] if B == 1 else torch.stack(args)).view(out_shape)
+    else:
+        if accumulate:
+            raise NotImplementedError("gno_b200: out= with a full-shape index is not supported")
+        index = index.contiguous()
+        dt = _dtype_id(src)
+        if want_arg:
+            arg = torch.empty(out_shape, dtype=torch.int64, device=src.device)
+        nbytes = ctypes.c_size_t()
+        check(lib.gno_scatter_elementwise_workspace(B, N, K, dt, red, ctypes.byref(nbytes)))
+        ws = _workspace(nbytes.value, src.device) if nbytes.value else None
+        with torch.cuda.device(src.device):
+            check(lib.gno_scatter_elementwise(_ptr(src), _ptr(index), B, E, K, _ptr(out), _ptr(arg),
+                                              N, dt, red, _ptr(ws), nbytes.value,
+                                              _stream(src.device)))
+    return (out, arg) if want_arg else out
+
+
+def gather_scatter(x, src_ids, dst_ids, dim_size, reduce="sum", return_arg=False, out=None):
+    """Fused message passing: scatter(x.index_select(0, src_ids), dst_ids, 0, dim_size, reduce)
+    without materialising the [E, F] messages (the C2/C3 hot path)."""
+    _need_cuda(x, src_ids, dst_ids)
+    red = _reduce_id(reduce)
+    want_arg = return_arg and red in (GNO_MIN, GNO_MAX)
+    plan = plan_cache.get(dst_ids, dim_size)
+    gidx = plan.sorted_ids(src_ids)
+    x2 = x if x.dim() == 2 else x.reshape(x.size(0), -1)
+    r = segment_reduce(plan, x2, reduce, gidx=gidx, eid=plan.perm, want_arg=want_arg,
+                       arg_fill=plan.E, out=out, accumulate=out is not None)
+    if x.dim() == 2:
+        return r
+    tail = list(x.shape[1:])
+    if want_arg:
+        return r[0].view([dim_size] + tail), r[1].view([dim_size] + tail)
+    return r.view([dim_size] + tail)
+
+
+def index_add(input, dim, index, source, inplace=False):
+    """Tensor.index_add_(dim, index, source) / torch.index_add on 2-D tensors, dim 0 or 1."""
+    _need_cuda(input, index, source)
+    if dim < 0:
+        dim += input.dim()
+    if input.dim() != 2 or source.dim() != 2 or dim not in (0, 1):
+        raise NotImplementedError("gno_b200.index_add covers 2-D tensors, dim 0/1")
+    out = input if inplace else input.clone()
+    if not out.is_contiguous():
+        raise ValueError("index_add_: input must be contiguous")
+    source = source.contiguous()
+    plan = plan_cache.get(index, out.size(dim))
+    if dim == 0:
+        segment_reduce(plan, source, "sum", gidx=plan.perm, out=out, accumulate=True)
+    else:
+        _segment_reduce_lastdim(plan, source, "sum", plan.perm, None, out, True, False, 0)
+    return out
+
+
+def index_select(input, dim, index):
+    """torch.index_select on 2-D tensors (dim 0: vectorised row gather; dim 1: last-dim gather)."""
+    _need_cuda(input, index)
+    if dim < 0:
+        dim += input.dim()
+    input = input.contiguous()
+    if input.dim() == 2 and dim == 0:
+        out = torch.empty((index.numel(), input.size(1)), dtype=input.dtype, device=input.device)
+        index = index.contiguous()
+        with torch.cuda.device(input.device):
+            check(lib.gno_gather_rows(_ptr(input), input.size(0), input.size(1) * input.element_size(),
+                                      _ptr(index), index.numel(), _ptr(out),
+                                      _stream(input.device)))
+        return out
+    if input.dim() == 2 and dim == 1:
+        # out[b, i] = input[b, index[i]]: a segment reduce with one edge per row
+        n = index.numel()
+        rowptr = _memo("iota_ptr", index, (), lambda: torch.arange(n + 1, dtype=torch.int64, device=index.device))
+        plan = _memo("rowptr_plan", rowptr, (n,), lambda: plan_from_rowptr(rowptr, n))
+        gidx = _memo("narrow", index, (), lambda: index.to(torch.int32))
+        out = torch.empty((input.size(0), n), dtype=input.dtype, device=input.device)
+        _segment_reduce_lastdim(plan, input, "sum", gidx, None, out, False, False, 0)
+        return out
+    raise NotImplementedError("gno_b200.index_select covers 2-D tensors, dim 0/1")
+
+
+# ----------------------------------------------------------------- segment_csr --
+def segment_csr(src, indptr, out=None, reduce="sum", return_arg=False):
+    """torch_scatter.segment_csr for 1-D indptr over dim 0 of src."""
+    _need_cuda(src, indptr)
+    if indptr.dim() != 1:
+        raise NotImplementedError("gno_b200.segment_csr covers 1-D indptr")
+    red = _reduce_id(reduce)
+    want_arg = return_arg and red in (GNO_MIN, GNO_MAX)
+    E = src.size(0)
+    plan = _memo("rowptr_plan", indptr, (E,), lambda: plan_from_rowptr(indptr, E))
+    x2 = src.contiguous().view(E, -1)
+    r = segment_reduce(plan, x2, reduce, want_arg=want_arg, arg_fill=E)
+    shape = [plan.N] + list(src.shape[1:])
+    if want_arg:
+        return r[0].view(shape), r[1].view(shape)
+    return r.view(shape)
+
+
+def gather_csr(src, indptr):
+    """torch_scatter.gather_csr: out[k] = src[row(k)] for 1-D indptr."""
+    _need_cuda(src, indptr)
+    counts = indptr[1:] - indptr[:-1]
+    rows = torch.repeat_interleave(torch.arange(counts.numel(), device=src.device), counts)
+    return index_select(src.contiguous().view(src.size(0), -1), 0, rows).view([rows.numel()] + list(src.shape[1:]))
+
+
+# ------------------------------------------------------------------------ spmm --
+def spmm(index, value, m, n, matrix, reduce="sum"):
+    """torch_sparse.spmm(index, value, m, n, matrix): COO [2, nnz] × dense [n, F] → [m, F]."""
+    _need_cuda(index, value, matrix)
+    squeeze = matrix.dim() == 1
+    mat = matrix.unsqueeze(-1) if squeeze else matrix
+    row, col = index[0], index[1]
+    plan = plan_cache.get(row, m)
+    gidx = plan.sorted_ids(col)
+    w = None
+    if value is not None:
+        v = value.to(mat.dtype).contiguous()
+
+        def _permute():
+            o = torch.empty_like(v)
+            with torch.cuda.device(v.device):
+                check(lib.gno_permute_rows(_ptr(v), _ptr(plan.perm), _ptr(o), v.numel(),
+                                           v.element_size(), _stream(v.device)))
+            return o
+        w = _memo("perm_val", value, (plan.rowptr.data_ptr(), str(mat.dtype)), _permute)
+    out = segment_reduce(plan, mat.contiguous(), reduce, gidx=gidx, weights=w)
+    return out.squeeze(-1) if squeeze else out
+
+
+def spmm_csr(rowptr, col, value, matrix, reduce="sum", return_arg=False):
+    """torch_sparse.matmul(SparseTensor(rowptr, col, value), matrix, reduce) on a given CSR."""
+    _need_cuda(rowptr, col, value, matrix)
+    red = _reduce_id(reduce)
+    want_arg = return_arg and red in (GNO_MIN, GNO_MAX)
+    nnz = col.numel()
+    plan = _memo("rowptr_plan", rowptr, (nnz,), lambda: plan_from_rowptr(rowptr, nnz))
+
+    def _narrow():
+        o = torch.empty(nnz, dtype=torch.int32, device=col.device)
+        c = col.contiguous()
+        with torch.cuda.device(col.device):
+            check(lib.gno_narrow_i64_to_i32(_ptr(c), _ptr(o), nnz, _stream(col.device)))
+        return o
+    gidx = col if col.dtype == torch.int32 else _memo("narrow", col, (), _narrow)
+    w = None if value is None else value.to(matrix.dtype).contiguous()
+    return segment_reduce(plan, matrix.contiguous(), reduce, gidx=gidx, weights=w,
+                          want_arg=want_arg, arg_fill=nnz)
+
+
+# ------------------------------------------------------- coalesce / transpose --
+def coo_order(index, n):
+    """(#inversions, #adjacent duplicates) of key=row*n+col — one host sync."""
+    status = torch.empty(2, dtype=torch.int64, device=index.device)
+    row, col = index[0].contiguous(), index[1].contiguous()
+    with torch.cuda.device(index.device):
+        check(lib.gno_coo_order_check(_ptr(row), _ptr(col), row.numel(), int(n), _ptr(status),
+                                      _stream(index.device)))
+    inv, dup = status.tolist()
+    return int(inv), int(dup)
+
+
+def _coalesce_impl(row, col, value, m, n, op, flags):
+    dev = row.device
+    E = row.numel()
+    red = _reduce_id(op)
+    K, dt, v2 = 0, GNO_F32, None
+    if value is not None:
+        v2 = value.contiguous().view(E, -1)
+        K, dt = v2.size(1), _dtype_id(v2)
+    out_row = torch.empty(E, dtype=torch.int64, device=dev)
+    out_col = torch.empty(E, dtype=torch.int64, device=dev)
+    out_val = torch.empty_like(v2) if v2 is not None else None
+    nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+    nbytes = ctypes.c_size_t()
+    check(lib.gno_coalesce_workspace(E, m, n, K, dt, ctypes.byref(nbytes)))
+    ws = _workspace(nbytes.value, dev)
+    row, col = row.contiguous(), col.contiguous()
+    with torch.cuda.device(dev):
+        check(lib.gno_coalesce(_ptr(row), _ptr(col), _ptr(v2), K, dt, E,
+                               int(m), int(n), red, flags, _ptr(out_row), _ptr(out_col),
+                               _ptr(out_val), _ptr(nnz), _ptr(ws), ws.numel(), _stream(dev)))
+    cnt = int(nnz.item())  # output size is data dependent: one sync, as upstream
+    index = torch.stack([out_row[:cnt], out_col[:cnt]])
+    if value is None:
+        return index, None
+    return index, out_val[:cnt].view([cnt] + list(value.shape[1:]))
+
+
+def coalesce(index, value, m, n, op="add"):
+    """torch_sparse.coalesce(index, value, m, n, op) → (index, value)."""
+    _need_cuda(index, value)
+    if index.dim() != 2 or index.size(0) != 2 or index.dtype != torch.int64:
+        raise ValueError("index must be an int64 [2, nnz] tensor")
+    if index.size(1) <= 1:
+        return index, value
+    inv, dup = coo_order(index, n)
+    if inv == 0 and dup == 0:
+        return index, value  # upstream early exit: already sorted and unique
+    return _coalesce_impl(index[0], index[1], value, m, n, op, 0)
+
+
+def transpose(index, value, m, n, coalesced=True):
+    """torch_sparse.transpose(index, value, m, n, coalesced) → (index, value) of the n×m matrix."""
+    _need_cuda(index, value)
+    row, col = index[0], index[1]
+    if not coalesced:
+        return torch.stack([col, row]), value
+    if index.size(1) == 0:
+        return torch.stack([col, row]), value
+    # A (row, col)-sorted input is already ascending in the transposed minor key:
+    # a stable sort on the new major key alone finishes the job.
+    inv, _ = coo_order(index, n)
+    flags = 1 if (inv == 0 and n <= (1 << 32)) else 0
+    return _coalesce_impl(col, row, value, n, m, "add", flags)
+
+
+# ------------------------------------------------------------------------ sort --
+def sort(input, dim=-1, descending=False, stable=True):
+    """torch.sort for float32 (always stable); returns (values, int64 indices)."""
+    _need_cuda(input)
+    if input.dtype != torch.float32:
+        raise GnoError("gno_b200.sort: float32 only")
+    if input.dim() == 0:
+        return input.clone(), torch.zeros((), dtype=torch.int64, device=input.device)
+    if dim < 0:
+        dim += input.dim()
+    x = input.contiguous()
+    outer = 1
+    for s in x.shape[:dim]:
+        outer *= s
+    inner = 1
+    for s in x.shape[dim + 1:]:
+        inner *= s
+    length = x.shape[dim]
+    vals = torch.empty_like(x)
+    idx = torch.empty(x.shape, dtype=torch.int64, device=x.device)
+    nbytes = ctypes.c_size_t()
+    check(lib.gno_sort_f32_workspace(outer, length, inner, ctypes.byref(nbytes)))
+    ws = _workspace(nbytes.value, x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gno_sort_f32(_ptr(x), _ptr(vals), _ptr(idx), outer, length, inner,
+                               1 if descending else 0, _ptr(ws), ws.numel(), _stream(x.device)))
+    return vals, idx
+
+
+def sort_pairs(keys, values=None, begin_bit=0, end_bit=None):
+    """Stable ascending radix sort of int32/int64 keys (as unsigned) with optional payload."""
+    _need_cuda(keys, values)
+    kb = keys.element_size()
+    if kb not in (4, 8):
+        raise ValueError("keys must be 4 or 8 bytes wide")
+    vb = 0 if values is None else values.element_size()
+    n = keys.numel()
+    keys = keys.contiguous()
+    values = values.contiguous() if values is not None else None
+    out_k = torch.empty_like(keys)
+    out_v = torch.empty_like(values) if values is not None else None
+    nbytes = ctypes.c_size_t()
+    check(lib.gno_sort_pairs_workspace(n, kb, vb, ctypes.byref(nbytes)))
+    ws = _workspace(nbytes.value, keys.device)
+    with torch.cuda.device(keys.device):
+        check(lib.gno_sort_pairs(_ptr(keys), _ptr(out_k), _ptr(values),
+                                 _ptr(out_v), n, kb, vb, begin_bit, kb * 8 if end_bit is None else end_bit,
+                                 _ptr(ws), ws.numel(), _stream(keys.device)))
+    return (out_k, out_v) if values is not None else out_k

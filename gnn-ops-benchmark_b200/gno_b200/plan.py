@@ -1,0 +1,151 @@
+"""Host side of the dst-sorted CSR plan (include/gno_b200.h: gno_plan_build).
+
+A plan is the reusable part of an aggregation: the stable argsort of the
+destination index (`perm`), the CSR `rowptr`, and the split table for rows
+longer than `split_len`.  GNN layers reuse one graph many times, so plans are
+cached on the identity of the index tensor — the same role the rowptr /
+csr2csc caches play inside torch_sparse.SparseTensor upstream.
+"""
+import collections
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, gno_csr, lib
+
+DEFAULT_SPLIT_LEN = 1024
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+class CSRPlan:
+    """dst-sorted CSR of a 1-D index.  All arrays live on the index's device."""
+
+    __slots__ = ("N", "E", "rowptr", "perm", "split_len", "n_heavy", "n_chunks", "max_len",
+                 "n_dropped", "hrow", "hcptr", "device", "_gidx_cache", "_keepalive")
+
+    def __init__(self):
+        self._gidx_cache = collections.OrderedDict()
+        self._keepalive = None
+
+    def csr(self, gidx, eid):
+        """The C struct for one launch. gidx/eid: int32 tensors or None (identity)."""
+        return gno_csr(self.N, self.E, self.rowptr.data_ptr(),
+                       gidx.data_ptr() if gidx is not None else None,
+                       eid.data_ptr() if eid is not None else None,
+                       self.split_len if self.n_heavy > 0 else 0, self.n_heavy, self.n_chunks,
+                       self.hrow.data_ptr() if self.n_heavy > 0 else None,
+                       self.hcptr.data_ptr() if self.n_heavy > 0 else None)
+
+    def sorted_ids(self, ids):
+        """int32 copy of `ids` (int64 [E]) reordered by the plan: ids[perm]. Cached."""
+        key = (ids.data_ptr(), ids._version, ids.numel())
+        hit = self._gidx_cache.get(key)
+        if hit is not None:
+            return hit[0]
+        out = torch.empty(self.E, dtype=torch.int32, device=self.device)
+        check(lib.gno_permute_i64_to_i32(_ptr(ids), _ptr(self.perm), _ptr(out), self.E,
+                                         _stream(self.device)))
+        self._gidx_cache[key] = (out, ids)
+        while len(self._gidx_cache) > 4:
+            self._gidx_cache.popitem(last=False)
+        return out
+
+
+def build_plan(index, num_rows, split_len=DEFAULT_SPLIT_LEN):
+    """Sort `index` (1-D int64, CUDA) by destination and build rowptr + split table."""
+    if not index.is_cuda:
+        raise _lib.GnoError("gno_b200 has no CPU path: index must be a CUDA tensor")
+    if index.dim() != 1 or index.dtype != torch.int64:
+        raise ValueError("plan index must be a 1-D int64 tensor")
+    index = index.contiguous()
+    dev = index.device
+    E, N = index.numel(), int(num_rows)
+    p = CSRPlan()
+    p.N, p.E, p.device, p.split_len = N, E, dev, int(split_len)
+    p.rowptr = torch.empty(N + 1, dtype=torch.int64, device=dev)
+    p.perm = torch.empty(max(E, 1), dtype=torch.int32, device=dev)[:E]
+    cap = int(lib.gno_plan_heavy_capacity(E, p.split_len))
+    hrow = torch.empty(cap, dtype=torch.int32, device=dev)
+    hcptr = torch.empty(cap + 1, dtype=torch.int64, device=dev)
+    info = torch.empty(4, dtype=torch.int64, device=dev)
+    nbytes = ctypes.c_size_t()
+    check(lib.gno_plan_workspace(E, N, ctypes.byref(nbytes)))
+    ws = _workspace(nbytes.value, dev)
+    with torch.cuda.device(dev):
+        check(lib.gno_plan_build(_ptr(index), E, N, p.split_len, _ptr(p.rowptr), _ptr(p.perm),
+                                 _ptr(info), _ptr(hrow), _ptr(hcptr), _ptr(ws), ws.numel(),
+                                 _stream(dev)))
+    p.n_dropped, p.max_len, p.n_heavy, p.n_chunks = (int(v) for v in info.tolist())  # one sync
+    p.hrow = hrow[:p.n_heavy]
+    p.hcptr = hcptr[:p.n_heavy + 1]
+    return p
+
+
+def plan_from_rowptr(rowptr, nnz, split_len=DEFAULT_SPLIT_LEN):
+    """Plan over a caller-supplied CSR rowptr (segment_csr / SparseTensor inputs)."""
+    if not rowptr.is_cuda:
+        raise _lib.GnoError("gno_b200 has no CPU path: rowptr must be a CUDA tensor")
+    rowptr = rowptr.contiguous().to(torch.int64)
+    dev = rowptr.device
+    N, E = rowptr.numel() - 1, int(nnz)
+    p = CSRPlan()
+    p.N, p.E, p.device, p.split_len = N, E, dev, int(split_len)
+    p.rowptr, p.perm = rowptr, None
+    cap = int(lib.gno_plan_heavy_capacity(E, p.split_len))
+    hrow = torch.empty(cap, dtype=torch.int32, device=dev)
+    hcptr = torch.empty(cap + 1, dtype=torch.int64, device=dev)
+    info = torch.empty(4, dtype=torch.int64, device=dev)
+    nbytes = ctypes.c_size_t()
+    check(lib.gno_plan_from_rowptr_workspace(N, E, ctypes.byref(nbytes)))
+    ws = _workspace(nbytes.value, dev)
+    with torch.cuda.device(dev):
+        check(lib.gno_plan_from_rowptr(_ptr(rowptr), N, E, p.split_len, _ptr(info), _ptr(hrow),
+                                       _ptr(hcptr), _ptr(ws), ws.numel(), _stream(dev)))
+    p.n_dropped, p.max_len, p.n_heavy, p.n_chunks = (int(v) for v in info.tolist())
+    p.hrow = hrow[:p.n_heavy]
+    p.hcptr = hcptr[:p.n_heavy + 1]
+    return p
+
+
+class PlanCache:
+    """LRU of plans keyed on the identity + version of the index tensor."""
+
+    def __init__(self, capacity=8):
+        self.capacity = capacity
+        self._d = collections.OrderedDict()
+        self.hits = 0
+        self.misses = 0
+
+    def get(self, index, num_rows, split_len=DEFAULT_SPLIT_LEN):
+        key = (index.data_ptr(), index._version, index.numel(), int(num_rows), int(split_len),
+               str(index.device))
+        p = self._d.get(key)
+        if p is not None:
+            self._d.move_to_end(key)
+            self.hits += 1
+            return p
+        self.misses += 1
+        p = build_plan(index, num_rows, split_len)
+        p._keepalive = index  # the key is a raw pointer: keep the tensor alive
+        self._d[key] = p
+        while len(self._d) > self.capacity:
+            self._d.popitem(last=False)
+        return p
+
+    def clear(self):
+        self._d.clear()
+
+
+plan_cache = PlanCache()

@@ -1,0 +1,32 @@
+"""Drop-in `torch_sparse` functions backed by the B200 library (gno_b200).
+
+Keeps the torch-sparse 0.6.12 functional signatures: `coalesce` as imported by
+the reference (op_bm_scripts/benchmark_sparse_coalesce.py:7,35-37), plus
+`transpose` and `spmm`, whose kernels the reference's sparse_transpose /
+sparse_spmm data rows time.  CUDA tensors only: there is no CPU fallback.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from gno_b200 import ops as _ops
+
+__version__ = "0.6.12+gno.b200"
+
+
+def coalesce(index: torch.Tensor, value: Optional[torch.Tensor], m: int, n: int,
+             op: str = "add") -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    return _ops.coalesce(index, value, m, n, op)
+
+
+def transpose(index: torch.Tensor, value: Optional[torch.Tensor], m: int, n: int,
+              coalesced: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    return _ops.transpose(index, value, m, n, coalesced)
+
+
+def spmm(index: torch.Tensor, value: torch.Tensor, m: int, n: int,
+         matrix: torch.Tensor) -> torch.Tensor:
+    return _ops.spmm(index, value, m, n, matrix)
+
+
+__all__ = ["coalesce", "transpose", "spmm"]

@@ -1,0 +1,243 @@
+/*
+ * gno_b200.h — C-ABI of the B200-native GNN aggregation path.
+ *
+ * This is the drop-in boundary: plain C, raw device pointers and sizes, a
+ * cudaStream_t passed as void*.  No torch types.  Every buffer (inputs,
+ * outputs, workspaces, plan arrays) is OWNED BY THE CALLER; the library never
+ * allocates device memory and never synchronises the device, so it composes
+ * with any allocator (torch's caching allocator in the Python host) and with
+ * CUDA-graph capture.  All functions return 0 on success or a gno_status
+ * code; gno_last_error() gives the thread-local message.
+ *
+ * The reference (ryienh/gnn-ops-benchmark) holds no native code: its kernels
+ * live in torch-scatter 2.0.9 / torch-sparse 0.6.12 / ATen 1.11.  Each entry
+ * point below names the reference call site whose work it replaces
+ * (file:line relative to the reference root).
+ */
+#ifndef GNO_B200_H
+#define GNO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNO_ABI_VERSION 1
+
+typedef void* gno_stream_t; /* a cudaStream_t */
+
+typedef enum gno_status {
+  GNO_OK = 0,
+  GNO_ERR_INVALID = 1,     /* bad argument (shape, alignment, enum) */
+  GNO_ERR_UNSUPPORTED = 2, /* valid request this build does not cover */
+  GNO_ERR_CUDA = 3,        /* a CUDA runtime call or launch failed */
+  GNO_ERR_WORKSPACE = 4    /* workspace pointer NULL or too small */
+} gno_status;
+
+typedef enum gno_dtype { GNO_F32 = 0, GNO_F16 = 1, GNO_BF16 = 2 } gno_dtype;
+
+/* Reductions of torch_scatter.scatter(..., reduce=) — the five the reference
+ * times: op_bm_scripts/benchmark_scatter_add.py:18, _mean.py:17, _max.py:17,
+ * _min.py:17, benchmark_scatter_multiply.py:44. */
+typedef enum gno_reduce {
+  GNO_SUM = 0,
+  GNO_MEAN = 1,
+  GNO_MUL = 2,
+  GNO_MIN = 3,
+  GNO_MAX = 4
+} gno_reduce;
+
+/* ---------------------------------------------------------------- info -- */
+
+int gno_abi_version(void);
+const char* gno_last_error(void);
+/* Number of kernels this library has launched in this process (monotonic;
+ * bench.py differences it around the timed region for "gpu_launches"). */
+int64_t gno_launch_count(void);
+
+/* ---------------------------------------------------------------- sort -- */
+/*
+ * Stable LSD radix sort of unsigned keys (4 or 8 bytes) with an optional
+ * payload (0, 4 or 8 bytes), ascending, over key bits [begin_bit, end_bit).
+ * On-chip ranking: warp match + shared-memory exchange; 8 bits per pass.
+ * keys_in/vals_in are not modified; results land in keys_out/vals_out.
+ * Replaces the CUB radix sort under torch.sort / argsort that the reference
+ * reaches through op_bm_scripts/benchmark_native_sort.py:29 and through
+ * torch_sparse.coalesce (op_bm_scripts/benchmark_sparse_coalesce.py:36).
+ */
+int gno_sort_pairs_workspace(int64_t n, int key_bytes, int val_bytes,
+                             size_t* bytes);
+int gno_sort_pairs(const void* keys_in, void* keys_out, const void* vals_in,
+                   void* vals_out, int64_t n, int key_bytes, int val_bytes,
+                   int begin_bit, int end_bit, void* ws, size_t ws_bytes,
+                   gno_stream_t stream);
+
+/*
+ * torch.sort(input, dim, stable=True) for fp32: input viewed as
+ * [outer, len, inner] (row-major), sorted along `len`.  Writes sorted values
+ * and int64 positions along `len`.  NaNs sort last, -0.0 == +0.0 (ties keep
+ * input order), matching torch's comparison semantics.
+ * Reference call site: op_bm_scripts/benchmark_native_sort.py:28-30.
+ */
+int gno_sort_f32_workspace(int64_t outer, int64_t len, int64_t inner,
+                           size_t* bytes);
+int gno_sort_f32(const float* in, float* out_values, int64_t* out_index,
+                 int64_t outer, int64_t len, int64_t inner, int descending,
+                 void* ws, size_t ws_bytes, gno_stream_t stream);
+
+/* ---------------------------------------------------------------- plan -- */
+/*
+ * Build the dst-sorted CSR plan of a 1-D int64 index vector (the
+ * "index"/edge_index[1] argument of torch_scatter.scatter,
+ * op_bm_scripts/benchmark_scatter_add.py:18 in its message-passing form):
+ *   perm   [E]   int32  stable argsort of index  (perm[k] = original edge id)
+ *   rowptr [N+1] int64  rowptr[i] = first sorted position with index >= i
+ *   info   [4]   int64  device scalars: [0] #entries outside [0,N) (those
+ *                        are dropped from every row), [1] max row length,
+ *                        [2] #rows longer than split_len, [3] #chunks those
+ *                        rows split into
+ *   hrow   [cap] int32  ids of rows longer than split_len (ascending)
+ *   hcptr  [cap+1] int64 exclusive prefix of their chunk counts
+ * cap = gno_plan_heavy_capacity(E, split_len).  Requires N < 2^31, E < 2^31.
+ */
+int64_t gno_plan_heavy_capacity(int64_t E, int64_t split_len);
+int gno_plan_workspace(int64_t E, int64_t N, size_t* bytes);
+int gno_plan_build(const int64_t* index, int64_t E, int64_t N,
+                   int64_t split_len, int64_t* rowptr, int32_t* perm,
+                   int64_t* info, int32_t* hrow, int64_t* hcptr, void* ws,
+                   size_t ws_bytes, gno_stream_t stream);
+/* Same heavy-row analysis for a caller-supplied CSR rowptr (torch_sparse
+ * SparseTensor / segment_csr inputs): fills info[1..3], hrow, hcptr. */
+int gno_plan_from_rowptr_workspace(int64_t N, int64_t E, size_t* bytes);
+int gno_plan_from_rowptr(const int64_t* rowptr, int64_t N, int64_t E,
+                         int64_t split_len,
+                         int64_t* info, int32_t* hrow, int64_t* hcptr,
+                         void* ws, size_t ws_bytes, gno_stream_t stream);
+
+/* out[k] = (int32) src[perm[k]]  — builds the sorted source-id array of the
+ * fused gather→scatter form (edge_index[0] reordered by the plan). */
+int gno_permute_i64_to_i32(const int64_t* src, const int32_t* perm,
+                           int32_t* out, int64_t E, gno_stream_t stream);
+/* out[k] = (int32) src[k] */
+int gno_narrow_i64_to_i32(const int64_t* src, int32_t* out, int64_t E,
+                          gno_stream_t stream);
+/* out[k, :] = src[perm[k], :] for rows of row_bytes bytes (value reorder). */
+int gno_permute_rows(const void* src, const int32_t* perm, void* out,
+                     int64_t E, int64_t row_bytes, gno_stream_t stream);
+
+/* ------------------------------------------------------ segment reduce -- */
+/*
+ * A dst-sorted graph as the kernels see it.  All pointers are device
+ * pointers owned by the caller.
+ */
+typedef struct gno_csr {
+  int64_t N;             /* destination rows */
+  int64_t E;             /* sorted edges */
+  const int64_t* rowptr; /* [N+1] */
+  const int32_t* gidx;   /* [E] row of x to gather for sorted edge k;
+                            NULL = k itself (segment_csr form) */
+  const int32_t* eid;    /* [E] value reported by arg outputs for edge k
+                            (original edge position); NULL = k */
+  int64_t split_len;     /* rows longer than this are split; 0 = never */
+  int64_t n_heavy;       /* info[2] */
+  int64_t n_chunks;      /* info[3] */
+  const int32_t* hrow;   /* [n_heavy] */
+  const int64_t* hcptr;  /* [n_heavy+1] */
+} gno_csr;
+
+/*
+ * out[i, :] = reduce over sorted edges k in row i of  w[k] * x[gidx[k], :]
+ * — the one kernel family behind scatter sum/mean/mul/min/max (+arg), the
+ * fused index_select→scatter_add / index_add_ gather-reduce, segment_csr and
+ * CSR spmm.  Warp-per-destination-row, atomic-free and deterministic; fp32
+ * accumulation for every dtype, one rounding at the end.
+ *
+ *   x        [x_rows, F] with row stride ldx elements
+ *   w        [E] per-sorted-edge weights in x's dtype, or NULL (spmm value)
+ *   out      [N, F] with row stride ldo elements
+ *   arg      [N, F] int64 (contiguous) or NULL; MIN/MAX only.  Winner =
+ *            lowest eid among equal values; rows with no winner get
+ *            arg_fill and out 0 (torch_scatter semantics)
+ *   accumulate  non-zero: combine with the values already in out
+ *            (index_add_ / out= forms; SUM and MUL only)
+ *   ws       >= gno_segment_reduce_workspace(...) bytes (split-row partials)
+ *
+ * Replaces: scatter_add/mean/max/min (op_bm_scripts/benchmark_scatter_add.py:18,
+ * _mean.py:17, _max.py:17, _min.py:17), scatter_(reduce="multiply")
+ * (benchmark_scatter_multiply.py:44), index_select→sum and
+ * index_add→index_select→sum (benchmark_fused_index_select_reduce.py:12-15,
+ * benchmark_fused_index_add_reduce.py:12-15), index_add_
+ * (benchmark_native_index_add_.py:13-16), torch.sparse.mm
+ * (benchmark_sparse_spmm.py:12-14).
+ */
+int gno_segment_reduce_workspace(const gno_csr* g, int64_t F, int dtype,
+                                 int reduce, int with_arg, size_t* bytes);
+int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows,
+                       int64_t ldx, const void* w, void* out, int64_t ldo,
+                       int64_t* arg, int64_t arg_fill, int64_t F, int dtype,
+                       int reduce, int accumulate, void* ws, size_t ws_bytes,
+                       gno_stream_t stream);
+
+/*
+ * Last-dim form: out[b, i] = reduce_{k in row i} x[b, gidx[k]] for x [B, L]
+ * (dim == last, 1-D index): index_select / index_add_ along dim 1
+ * (benchmark_native_index_add_.py:62, benchmark_fused_*_reduce.py dim=1).
+ * Source rows are staged through shared memory.
+ */
+int gno_segment_reduce_lastdim(const gno_csr* g, const void* x, int64_t B,
+                               int64_t L, int64_t ldx, void* out, int64_t ldo,
+                               int64_t* arg, int64_t arg_fill, int dtype,
+                               int reduce, int accumulate,
+                               gno_stream_t stream);
+
+/* out[k, :] = x[index[k], :]  (row gather with 128-bit accesses): the
+ * un-fused index_select of benchmark_native_index_select.py:12-15. */
+int gno_gather_rows(const void* x, int64_t x_rows, int64_t row_bytes,
+                    const int64_t* index, int64_t n_index, void* out,
+                    gno_stream_t stream);
+
+/* -------------------------------------------- element-wise index form -- */
+/*
+ * torch_scatter.scatter with a FULL-SHAPE index (same shape as src) — what
+ * op_bm_scripts/benchmark_scatter_{add,max,min,mean}.py:60-84 pass: src and
+ * index viewed as [B, E, K], out as [B, N, K]:
+ *   out[b, index[b,e,k], k] = reduce(src[b,e,k]).
+ * Deterministic values for MIN/MAX and deterministic arg (lowest e among
+ * ties); SUM/MEAN/MUL accumulate in fp32 in `ws` and round once.
+ */
+int gno_scatter_elementwise_workspace(int64_t B, int64_t N, int64_t K,
+                                      int dtype, int reduce, size_t* bytes);
+int gno_scatter_elementwise(const void* src, const int64_t* index, int64_t B,
+                            int64_t E, int64_t K, void* out, int64_t* arg,
+                            int64_t N, int dtype, int reduce, void* ws,
+                            size_t ws_bytes, gno_stream_t stream);
+
+/* ------------------------------------------------- coalesce / transpose -- */
+/*
+ * torch_sparse.coalesce(index, value, m, n, op): sort COO entries by
+ * (row, col), merge duplicates (op = SUM/MEAN/MIN/MAX/MUL over `value`
+ * rows of K elements).  Outputs are sized for E entries; *nnz_out (device
+ * int64) receives the merged count.  Passing (col,row,n,m) gives
+ * torch_sparse.transpose.  flags: bit0 = input known sorted by `row`
+ * (sort only the low key bits).
+ * Reference call site: op_bm_scripts/benchmark_sparse_coalesce.py:35-37;
+ * transpose: data/sparse_transpose.csv rows (torch_sparse.transpose).
+ */
+int gno_coalesce_workspace(int64_t E, int64_t m, int64_t n, int64_t K,
+                           int dtype, size_t* bytes);
+int gno_coalesce(const int64_t* row, const int64_t* col, const void* value,
+                 int64_t K, int dtype, int64_t E, int64_t m, int64_t n,
+                 int reduce, int flags, int64_t* out_row, int64_t* out_col,
+                 void* out_value, int64_t* nnz_out, void* ws, size_t ws_bytes,
+                 gno_stream_t stream);
+/* Device check used for torch_sparse's early exit: status[0] = #inversions
+ * of key=row*n+col, status[1] = #adjacent duplicates. */
+int gno_coo_order_check(const int64_t* row, const int64_t* col, int64_t E,
+                        int64_t n, int64_t* status, gno_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNO_B200_H */
