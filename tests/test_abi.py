@@ -1,0 +1,81 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every function that
+include/gno_b200.h declares, validates arguments without a GPU, and the torch_scatter /
+torch_sparse shims keep the upstream signatures and refuse CPU tensors (no fallback)."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "gno_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gno_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    from gno_b200 import _lib
+    names = declared_functions()
+    assert len(names) >= 20
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in gno_b200.h but not exported"
+    assert set(names) == set(_lib.PROTOTYPES), "ctypes prototypes out of sync with the header"
+
+
+def test_abi_argument_validation_without_gpu():
+    from gno_b200 import _lib
+    lib = _lib.lib
+    assert lib.gno_abi_version() == 1
+    n = ctypes.c_size_t()
+    assert lib.gno_sort_pairs_workspace(1000, 4, 4, ctypes.byref(n)) == 0 and n.value > 8000
+    assert lib.gno_sort_pairs_workspace(1000, 3, 4, ctypes.byref(n)) == 1  # GNO_ERR_INVALID
+    assert b"key_bytes" in lib.gno_last_error()
+    assert lib.gno_plan_workspace(1 << 31, 10, ctypes.byref(n)) == 1
+    assert lib.gno_plan_workspace(10, 10, ctypes.byref(n)) == 0
+    assert lib.gno_plan_heavy_capacity(1000, 100) == 11
+    with pytest.raises(_lib.GnoError):
+        _lib.check(lib.gno_coalesce_workspace(-1, 1, 1, 1, 0, ctypes.byref(n)))
+    assert lib.gno_launch_count() >= 0
+
+
+def test_shim_signatures_match_upstream():
+    import torch_scatter
+    import torch_sparse
+    for name in ("scatter_sum", "scatter_add", "scatter_mul", "scatter_mean", "scatter_min", "scatter_max"):
+        assert list(inspect.signature(getattr(torch_scatter, name)).parameters) == ["src", "index", "dim", "out", "dim_size"]
+    sig = inspect.signature(torch_scatter.scatter)
+    assert list(sig.parameters) == ["src", "index", "dim", "out", "dim_size", "reduce"]
+    assert sig.parameters["dim"].default == -1 and sig.parameters["reduce"].default == "sum"
+    assert list(inspect.signature(torch_scatter.segment_csr).parameters) == ["src", "indptr", "out", "reduce"]
+    assert list(inspect.signature(torch_sparse.coalesce).parameters) == ["index", "value", "m", "n", "op"]
+    assert list(inspect.signature(torch_sparse.transpose).parameters) == ["index", "value", "m", "n", "coalesced"]
+    assert list(inspect.signature(torch_sparse.spmm).parameters) == ["index", "value", "m", "n", "matrix"]
+    with pytest.raises(ValueError):
+        torch_scatter.scatter(torch.ones(2, 2), torch.zeros(2, dtype=torch.int64), reduce="median")
+
+
+def test_no_cpu_fallback():
+    import gno_b200
+    import torch_scatter
+    import torch_sparse
+    with pytest.raises(gno_b200.GnoError):
+        torch_scatter.scatter_add(torch.ones(4, 2), torch.zeros(4, dtype=torch.int64), dim=0)
+    with pytest.raises(gno_b200.GnoError):
+        torch_sparse.coalesce(torch.zeros(2, 3, dtype=torch.int64), torch.ones(3), 2, 2)
+    with pytest.raises(gno_b200.GnoError):
+        gno_b200.sort(torch.ones(4))
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through the oracle."""
+    pkg = os.path.join(ROOT, "gnn-ops-benchmark_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(d, f)).read().lower(), os.path.join(d, f)

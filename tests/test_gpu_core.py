@@ -10,11 +10,16 @@ pytestmark = pytest.mark.gpu
 TOL = {torch.float32: 1e-5, torch.float16: 1e-2, torch.bfloat16: 1e-2}
 
 
-def close(a, b, dtype):
+def close(a, b, dtype, scale=None):
+    """|a - b| <= tol * scale, where scale is the magnitude the rounding error is relative to:
+    |b| itself, or (for sums, whose terms cancel) the sum of |terms| per output element."""
     a, b = a.float().cpu(), b.float().cpu()
     tol = TOL[dtype]
     assert a.shape == b.shape
-    assert torch.allclose(a, b, rtol=tol, atol=tol), f"max abs diff {(a - b).abs().max()}"
+    scale = b.abs() if scale is None else torch.maximum(scale.float().cpu(), b.abs())
+    err = (a - b).abs()
+    bad = err > tol * scale + 1e-30
+    assert not bad.any(), f"max err/scale {(err / (scale + 1e-30)).max():.3e} > {tol}"
 
 
 @pytest.mark.parametrize("n,bits", [(0, 32), (1, 32), (1000, 32), (4096, 32), (4097, 32), (100_000, 17),
@@ -101,9 +106,12 @@ def test_scatter_1d_index(cuda, dtype, reduce, E, N, F):
         assert torch.equal(out.cpu(), want), "min/max values must be bit-exact"
         assert torch.equal(arg.cpu(), want_arg), "arg must be bit-exact"
     else:
-        if reduce == "mul" and E // N > 200:
-            pytest.skip("product over/underflows")
-        close(got, want, dtype)
+        if reduce == "mul" and E // N > 50:
+            pytest.skip("rounding of a long product exceeds rel 1e-5 in any order")
+        scale = None
+        if reduce in ("sum", "mean"):  # error of a sum is relative to the sum of |terms|
+            scale = oracle.scatter(src.float().abs(), idx, 0, N, reduce)[0]
+        close(got, want, dtype, scale)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -139,7 +147,8 @@ def test_gather_scatter_split_rows(cuda, dtype, reduce, E, N, F, split):
         assert torch.equal(r[0].cpu(), want)
         assert torch.equal(r[1].cpu(), want_arg)
     else:
-        close(r, want, dtype)
+        scale = oracle.gather_scatter(x.float().abs(), src_ids, dst, N, reduce)[0]
+        close(r, want, dtype, scale)
 
 
 def test_empty_rows_and_sentinels(cuda):

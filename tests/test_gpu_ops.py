@@ -1,0 +1,345 @@
+"""GPU parity of the remaining operators against the CPU oracle: full-shape-index scatter
+(what the reference scripts pass), last-dim forms, index_add / index_select, spmm,
+segment_csr, coalesce / transpose, sort.  Index outputs bit-exact; float sums to tolerance."""
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.float16: 1e-2, torch.bfloat16: 1e-2}
+
+
+def close(a, b, dtype, scale=None):
+    a, b = a.float().cpu(), b.float().cpu()
+    tol = TOL[dtype]
+    assert a.shape == b.shape
+    scale = b.abs() if scale is None else torch.maximum(scale.float().cpu(), b.abs())
+    err = (a - b).abs()
+    assert not (err > tol * scale + 1e-30).any(), f"max err/scale {(err / (scale + 1e-30)).max():.3e}"
+
+
+# ---- the reference scripts' call shape: 2-D fp16 src, full-shape int64 index, dim 0/1 -----------
+# (op_bm_scripts/benchmark_scatter_add.py:60-84; same in _max/_min/_mean)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("reduce", ["sum", "mean", "mul", "min", "max"])
+@pytest.mark.parametrize("L,rf,dim", [(223, 1, 0), (223, 1, 1), (300, 4, 0), (300, 8, 1), (64, 2, -1)])
+def test_scatter_full_shape_index(cuda, dtype, reduce, L, rf, dim):
+    import torch_scatter
+    g = torch.Generator().manual_seed(L * 10 + rf)
+    src = torch.rand(L, L, generator=g)
+    if reduce == "mul":
+        src = src * 0.5 + 0.75
+    if reduce in ("min", "max"):
+        src = (src * 16).round() / 16
+    src = src.to(dtype)
+    idx = torch.randint(0, max(L // rf, 1), (L, L), generator=g)
+    fn = getattr(torch_scatter, "scatter_" + {"sum": "add"}.get(reduce, reduce))
+    got = fn(src.to(cuda), idx.to(cuda), dim=dim)
+    want, want_arg = oracle.scatter(src, idx, dim, None, reduce)
+    if reduce in ("min", "max"):
+        assert isinstance(got, tuple)
+        assert torch.equal(got[0].cpu(), want)
+        assert torch.equal(got[1].cpu(), want_arg)
+    else:
+        scale = oracle.scatter(src.float().abs(), idx, dim, None, reduce)[0] if reduce != "mul" else None
+        close(got, want, dtype, scale)
+
+
+def test_scatter_full_shape_3d(cuda):
+    import gno_b200
+    g = torch.Generator().manual_seed(3)
+    src = torch.randn(5, 40, 7, generator=g)
+    idx = torch.randint(0, 9, (5, 40, 7), generator=g)
+    for red in ("sum", "max", "min", "mean"):
+        got = gno_b200.scatter(src.to(cuda), idx.to(cuda), 1, None, 9, red, return_arg=True)
+        want, warg = oracle.scatter(src, idx, 1, 9, red)
+        if red in ("max", "min"):
+            assert torch.equal(got[0].cpu(), want) and torch.equal(got[1].cpu(), warg)
+        else:
+            close(got, want, torch.float32, oracle.scatter(src.abs(), idx, 1, 9, red)[0])
+
+
+# ---- 1-D index along other dims ----------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("reduce", ["sum", "mean", "max", "min", "mul"])
+def test_scatter_1d_index_lastdim(cuda, dtype, reduce):
+    import gno_b200
+    g = torch.Generator().manual_seed(11)
+    B, E, N = 37, 500, 41
+    src = torch.rand(B, E, generator=g)
+    if reduce in ("min", "max"):
+        src = (src * 8).round() / 8
+    if reduce == "mul":
+        src = src * 0.5 + 0.75
+    src = src.to(dtype)
+    idx = torch.randint(0, N, (E,), generator=g)
+    got = gno_b200.scatter(src.to(cuda), idx.to(cuda), 1, None, N, reduce, return_arg=True)
+    want, warg = oracle.scatter(src, idx, 1, N, reduce)
+    if reduce in ("min", "max"):
+        assert torch.equal(got[0].cpu(), want) and torch.equal(got[1].cpu(), warg)
+    else:
+        close(got, want, dtype, oracle.scatter(src.float().abs(), idx, 1, N, reduce)[0] if reduce != "mul" else None)
+
+
+def test_scatter_1d_index_middle_dim(cuda):
+    import gno_b200
+    g = torch.Generator().manual_seed(12)
+    src = torch.randn(3, 200, 6, generator=g)
+    idx = torch.randint(0, 17, (200,), generator=g)
+    for red in ("sum", "max"):
+        got = gno_b200.scatter(src.to(cuda), idx.to(cuda), 1, None, 17, red, return_arg=True)
+        want, warg = oracle.scatter(src, idx, 1, 17, red)
+        if red == "max":
+            assert torch.equal(got[0].cpu(), want) and torch.equal(got[1].cpu(), warg)
+        else:
+            close(got, want, torch.float32, oracle.scatter(src.abs(), idx, 1, 17, red)[0])
+
+
+def test_scatter_expanded_index_and_dim_size_none(cuda):
+    """PyG-style call: index expanded with stride 0, dim_size=None → index.max()+1."""
+    import torch_scatter
+    g = torch.Generator().manual_seed(13)
+    src = torch.randn(300, 12, generator=g)
+    idx = torch.randint(0, 20, (300,), generator=g)
+    got = torch_scatter.scatter(src.to(cuda), idx.to(cuda).view(-1, 1).expand(-1, 12), dim=0, reduce="sum")
+    want, _ = oracle.scatter(src, idx, 0, None, "sum")
+    assert got.shape == want.shape
+    close(got, want, torch.float32, oracle.scatter(src.abs(), idx, 0, None, "sum")[0])
+    # out= accumulation (index_add_-like)
+    base = torch.randn(20, 12, generator=g)
+    got = torch_scatter.scatter_add(src.to(cuda), idx.to(cuda), dim=0, out=base.clone().to(cuda))
+    close(got, base + want, torch.float32, base.abs() + oracle.scatter(src.abs(), idx, 0, 20, "sum")[0])
+
+
+# ---- native-torch spellings: index_add_, index_select -----------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("dim", [0, 1])
+def test_index_add(cuda, dtype, dim):
+    import gno_b200
+    g = torch.Generator().manual_seed(21 + dim)
+    L = 257
+    inp = torch.rand(L, L, generator=g).to(dtype)
+    other = torch.rand(L, L, generator=g).to(dtype)
+    idx = torch.randint(0, L, (L,), generator=g)
+    got = gno_b200.index_add(inp.to(cuda), dim, idx.to(cuda), other.to(cuda))
+    want = oracle.index_add(inp, dim, idx, other)
+    scale = oracle.index_add(inp.float().abs(), dim, idx, other.float().abs())
+    close(got, want, dtype, scale)
+    native = torch.index_add(inp.float(), dim, idx, other.float())
+    close(got, native, dtype, scale)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dim", [0, 1])
+@pytest.mark.parametrize("L,rf", [(129, 1), (250, 4), (67, 8)])
+def test_index_select(cuda, dtype, dim, L, rf):
+    import gno_b200
+    g = torch.Generator().manual_seed(L)
+    inp = torch.rand(L, L, generator=g).to(dtype)
+    idx = torch.randint(0, L, (max(L // rf, 1),), generator=g)
+    got = gno_b200.index_select(inp.to(cuda), dim, idx.to(cuda))
+    assert torch.equal(got.cpu(), torch.index_select(inp, dim, idx))
+
+
+# ---- spmm / segment_csr ------------------------------------------------------------------------
+def _random_csr(M, Ncols, nnz, g):
+    row = torch.randint(0, M, (nnz,), generator=g).sort().values
+    col = torch.randint(0, Ncols, (nnz,), generator=g)
+    rowptr = torch.zeros(M + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(torch.bincount(row, minlength=M), 0)
+    return row, col, rowptr
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("reduce", ["sum", "mean", "min", "max"])
+@pytest.mark.parametrize("M,F,nnz", [(100, 256, 5000), (1000, 33, 20000), (10, 64, 40000)])
+def test_spmm_csr(cuda, dtype, reduce, M, F, nnz):
+    import gno_b200
+    gno_b200.clear_caches()
+    g = torch.Generator().manual_seed(M + F)
+    row, col, rowptr = _random_csr(M, 77, nnz, g)
+    mat = torch.randn(77, F, generator=g)
+    if reduce in ("min", "max"):
+        mat = (mat * 2).round() / 2
+    mat = mat.to(dtype)
+    value = torch.rand(nnz, generator=g).to(dtype) if reduce in ("sum", "mean") else None
+    want, warg = oracle.spmm_csr(rowptr, col, value, mat, reduce)
+    got = gno_b200.spmm_csr(rowptr.to(cuda), col.to(cuda), value.to(cuda) if value is not None else None,
+                            mat.to(cuda), reduce, return_arg=True)
+    if reduce in ("min", "max"):
+        assert torch.equal(got[0].cpu(), want) and torch.equal(got[1].cpu(), warg)
+    else:
+        v = value.float().abs() if value is not None else None
+        scale = oracle.spmm_csr(rowptr, col, v, mat.float().abs(), reduce)[0]
+        close(got, want, dtype, scale)
+
+
+def test_spmm_coo_matches_reference_formulation(cuda):
+    """torch_sparse.spmm(index, value, m, n, matrix) vs the oracle and vs torch.sparse.mm
+    (the call benchmark_sparse_spmm.py:12-14 times)."""
+    import torch_sparse
+    g = torch.Generator().manual_seed(5)
+    m, n, F, nnz = 300, 200, 48, 6000
+    index = torch.stack([torch.randint(0, m, (nnz,), generator=g), torch.randint(0, n, (nnz,), generator=g)])
+    value = torch.rand(nnz, generator=g)
+    mat = torch.randn(n, F, generator=g)
+    got = torch_sparse.spmm(index.to(cuda), value.to(cuda), m, n, mat.to(cuda))
+    want = oracle.spmm(index, value, m, n, mat)
+    native = torch.sparse.mm(torch.sparse_coo_tensor(index, value, (m, n)), mat)
+    scale = oracle.spmm(index, value, m, n, mat.abs())
+    close(got, want, torch.float32, scale)
+    close(got, native, torch.float32, scale)
+
+
+@pytest.mark.parametrize("reduce", ["sum", "mean", "min", "max"])
+def test_segment_csr(cuda, reduce):
+    import torch_scatter
+    g = torch.Generator().manual_seed(8)
+    src = (torch.randn(1000, 5, generator=g) * 4).round() / 4
+    indptr = torch.tensor([0, 0, 10, 10, 500, 999, 1000])
+    want, warg = oracle.spmm_csr(indptr, torch.arange(1000), None, src, reduce)
+    got = torch_scatter.segment_csr(src.to(cuda), indptr.to(cuda), reduce=reduce)
+    if reduce in ("min", "max"):
+        assert torch.equal(got.cpu(), want)
+        v, a = torch_scatter.segment_max_csr(src.to(cuda), indptr.to(cuda)) if reduce == "max" else \
+            torch_scatter.segment_min_csr(src.to(cuda), indptr.to(cuda))
+        assert torch.equal(v.cpu(), want) and torch.equal(a.cpu(), warg)
+    else:
+        close(got, want, torch.float32, oracle.spmm_csr(indptr, torch.arange(1000), None, src.abs(), reduce)[0])
+
+
+# ---- coalesce / transpose ----------------------------------------------------------------------
+def _dup_coo(m, n, nnz, rf, g):
+    """COO with duplicates built like benchmark_sparse_coalesce.py:129-159 (index permuted, value not)."""
+    index_ = torch.stack([torch.randint(0, m, (nnz,), generator=g), torch.randint(0, n, (nnz,), generator=g)])
+    value_ = torch.rand(nnz, generator=g)
+    index = torch.cat([index_] * rf, dim=1)
+    value = torch.cat([value_] * rf)
+    index = index.index_select(1, torch.randperm(index.shape[1], generator=g))
+    return index, value
+
+
+@pytest.mark.parametrize("m,n,nnz,rf", [(100, 100, 2000, 2), (5000, 3, 20000, 4), (1 << 20, 1 << 20, 50000, 8),
+                                        (7, 100000, 30000, 1)])
+@pytest.mark.parametrize("op", ["add", "mean", "max"])
+def test_coalesce(cuda, m, n, nnz, rf, op):
+    import torch_sparse
+    g = torch.Generator().manual_seed(nnz + rf)
+    index, value = _dup_coo(m, n, nnz, rf, g)
+    gi, gv = torch_sparse.coalesce(index.to(cuda), value.to(cuda), m, n, op)
+    wi, wv = oracle.coalesce(index, value, m, n, op)
+    assert torch.equal(gi.cpu(), wi), "coalesced indices must be bit-exact"
+    close(gv, wv, torch.float32, oracle.coalesce(index, value.abs(), m, n, "add" if op == "add" else op)[1])
+    if op == "add":  # independent formulation: Tensor.coalesce()
+        nat = torch.sparse_coo_tensor(index, value, (m, n)).coalesce()
+        assert torch.equal(gi.cpu(), nat.indices())
+        close(gv, nat.values(), torch.float32)
+
+
+def test_coalesce_edge_cases(cuda):
+    import torch_sparse
+    # value=None, K>1 values, already-sorted early exit returns the same tensors, empty input
+    g = torch.Generator().manual_seed(1)
+    index, _ = _dup_coo(50, 60, 500, 2, g)
+    gi, gv = torch_sparse.coalesce(index.to(cuda), None, 50, 60)
+    assert gv is None and torch.equal(gi.cpu(), oracle.coalesce(index, None, 50, 60)[0])
+    val = torch.randn(index.shape[1], 3, generator=g)
+    gi, gv = torch_sparse.coalesce(index.to(cuda), val.to(cuda), 50, 60)
+    wi, wv = oracle.coalesce(index, val, 50, 60)
+    assert torch.equal(gi.cpu(), wi)
+    close(gv, wv, torch.float32, oracle.coalesce(index, val.abs(), 50, 60)[1])
+    si, sv = gi, gv
+    ri, rv = torch_sparse.coalesce(si, sv, 50, 60)
+    assert ri.data_ptr() == si.data_ptr() and rv.data_ptr() == sv.data_ptr()
+    ei, ev = torch_sparse.coalesce(torch.zeros(2, 0, dtype=torch.int64, device=cuda),
+                                   torch.zeros(0, device=cuda), 5, 5)
+    assert ei.shape == (2, 0) and ev.shape == (0,)
+
+
+@pytest.mark.parametrize("m,n,nnz", [(300, 200, 5000), (5, 100000, 20000), (100000, 5, 20000)])
+def test_transpose(cuda, m, n, nnz):
+    import torch_sparse
+    g = torch.Generator().manual_seed(nnz)
+    index, value = _dup_coo(m, n, nnz, 1, g)
+    # generic path: unsorted input with duplicates
+    gi, gv = torch_sparse.transpose(index.to(cuda), value.to(cuda), m, n)
+    wi, wv = oracle.transpose(index, value, m, n)
+    assert torch.equal(gi.cpu(), wi)
+    close(gv, wv, torch.float32)
+    # fast path: coalesced input → stable sort on the new major key only; exact value permutation
+    ci, cv = oracle.coalesce(index, value, m, n)
+    gi, gv = torch_sparse.transpose(ci.to(cuda), cv.to(cuda), m, n)
+    wi, wv = oracle.transpose(ci, cv, m, n)
+    assert torch.equal(gi.cpu(), wi)
+    assert torch.equal(gv.cpu(), wv), "transposing a coalesced matrix only permutes values"
+    # involution
+    bi, bv = torch_sparse.transpose(gi, gv, n, m)
+    assert torch.equal(bi.cpu(), ci) and torch.equal(bv.cpu(), cv)
+    ui, uv = torch_sparse.transpose(index.to(cuda), value.to(cuda), m, n, coalesced=False)
+    assert torch.equal(ui.cpu(), index.flip(0)) and torch.equal(uv.cpu(), value)
+
+
+# ---- sort --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,dim", [((100_003,), 0), ((300, 500), 1), ((300, 500), 0), ((20, 30, 40), 1),
+                                       ((20, 30, 40), -1), ((1,), 0), ((5, 1), 0)])
+@pytest.mark.parametrize("descending", [False, True])
+def test_sort_f32(cuda, shape, dim, descending):
+    import gno_b200
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    x = torch.where(torch.rand(*shape, generator=g) < 0.3, (x * 2).round() / 2, x)  # ties
+    flat = x.view(-1)
+    flat[::17] = 0.0
+    flat[5::29] = -0.0
+    flat[3::41] = float("nan")
+    flat[7::97] = float("inf")
+    flat[9::101] = -float("inf")
+    v, i = gno_b200.sort(x.to(cuda), dim, descending)
+    wv, wi = oracle.sort(x, dim, descending)
+    assert torch.equal(i.cpu(), wi), "sort indices must be bit-exact"
+    assert torch.equal(v.cpu().view(torch.int32), wv.view(torch.int32)), "sorted values must be bit-exact"
+    tv, ti = torch.sort(x, dim=dim, descending=descending, stable=True)
+    assert torch.equal(i.cpu(), ti)
+    assert torch.equal(v.cpu().view(torch.int32), tv.view(torch.int32))
+
+
+# ---- golden vectors made by the reference's own op functions -----------------------------------
+def test_golden_native_ops(cuda):
+    """tests/golden/native_ops.npz was produced by executing the op functions defined in the
+    reference scripts (see tests/golden/make_golden.py) on seeded CPU inputs."""
+    import os
+    import numpy as np
+    import gno_b200
+    path = os.path.join(os.path.dirname(__file__), "golden", "native_ops.npz")
+    z = np.load(path)
+    t = lambda k: torch.from_numpy(z[k])  # noqa: E731
+    # op_native_sort (benchmark_native_sort.py:28-30)
+    for tag in ("sort1d", "sort2d_d0", "sort2d_d1"):
+        dim = int(z[tag + "_dim"])
+        v, i = gno_b200.sort(t(tag + "_in").to(cuda), dim)
+        assert torch.equal(i.cpu(), t(tag + "_idx")) and torch.equal(v.cpu(), t(tag + "_val")), tag
+    # op_native_index_add_ (benchmark_native_index_add_.py:13-16), fp16 like the script
+    got = gno_b200.index_add(t("iadd_in").to(cuda), 1, t("iadd_index").to(cuda), t("iadd_src").to(cuda))
+    close(got, t("iadd_out"), torch.float16, t("iadd_scale"))
+    # index_select (benchmark_native_index_select.py:12-15)
+    for dim in (0, 1):
+        got = gno_b200.index_select(t("isel_in").to(cuda), dim, t("isel_index").to(cuda))
+        assert torch.equal(got.cpu(), t(f"isel_out_d{dim}"))
+    # fused index_select→sum (benchmark_fused_index_select_reduce.py:12-15)
+    got = gno_b200.index_select(t("isel_in").to(cuda), 0, t("isel_index").to(cuda)).float().sum()
+    assert abs(float(got) - float(z["isel_sum_d0"])) <= 1e-2 * float(z["isel_abs_sum_d0"])
+    # op_native_smm (benchmark_sparse_spmm.py:12-14)
+    got = gno_b200.spmm(t("smm_index").to(cuda), t("smm_value").to(cuda), int(z["smm_m"]), int(z["smm_n"]),
+                        t("smm_B").to(cuda))
+    close(got, t("smm_out"), torch.float32, t("smm_scale"))
+    # op_native_coalesce (benchmark_sparse_coalesce.py:40-42)
+    gi, gv = gno_b200.coalesce(t("coal_index").to(cuda), t("coal_value").to(cuda), int(z["coal_m"]), int(z["coal_n"]))
+    assert torch.equal(gi.cpu(), t("coal_out_index"))
+    close(gv, t("coal_out_value"), torch.float32)
+    # op_native_scatter_add_ / scatter_(reduce=multiply) (benchmark_scatter_add.py:22-25, _multiply.py:42-45)
+    got = gno_b200.scatter(t("sadd_src").to(cuda), t("sadd_idx").to(cuda), 0, None, t("sadd_src").shape[0], "sum")
+    close(got, t("sadd_out"), torch.float16, t("sadd_scale"))
+    got = gno_b200.scatter(t("smul_src").to(cuda), t("smul_idx").to(cuda), -1, None, t("smul_src").shape[-1], "mul")
+    close(got, t("smul_out"), torch.float32)
