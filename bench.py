@@ -313,7 +313,8 @@ def run_ours(args):
                        "features": F, "index": "int64 edge_index -> cached dst-sorted CSR plan (int32)",
                        "l2": "inputs larger than L2 (x + col + out >> 126 MB); no flush needed",
                        "plan_build_ms": plan_ms, "max_row_len": plan.max_len,
-                       "split_rows": plan.n_heavy,
+                       "chunk_len": plan.chunk_len, "rows_cut_by_chunks": plan.n_span,
+                       "empty_rows": plan.n_empty,
                        "parallelism": f"dst-partitioned x{world}, NCCL all-gather of x" if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

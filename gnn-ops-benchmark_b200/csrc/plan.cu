@@ -1,5 +1,6 @@
-// Plan builder: dst-sorted CSR (rowptr + perm) of a 1-D index vector, plus
-// the split table for rows longer than split_len (power-law graphs).
+// Plan builder: dst-sorted CSR (rowptr + perm + per-edge row) of a 1-D index
+// vector, plus the lists of rows the finish pass must touch (rows cut by a
+// chunk boundary, empty rows).
 #include "common.cuh"
 
 namespace gno {
@@ -47,80 +48,65 @@ __global__ void rowptr_kernel(const uint32_t* __restrict__ keys, int64_t* __rest
   }
 }
 
-// flag[r] = 1 if row r is longer than split_len; also the max row length.
-__global__ void heavy_flag_kernel(const int64_t* __restrict__ rowptr, int32_t* __restrict__ flag,
-                                  int64_t N, int64_t split_len, int64_t* __restrict__ info) {
+// Row classes for chunk_len-edge chunks: a row "spans" when a chunk boundary
+// cuts it (its partial sums are combined by the finish pass); empty rows are
+// zero-filled by the finish pass.  MODE 0: count into info[1..3];
+// MODE 1: write flags for the compaction scans.
+template <int MODE>
+__global__ void row_class_kernel(const int64_t* __restrict__ rowptr, int64_t N, int64_t chunk_len,
+                                 int32_t* __restrict__ span_flag, int32_t* __restrict__ empty_flag,
+                                 int64_t* __restrict__ info) {
   long long mx = 0;
+  int n_span = 0, n_empty = 0;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < N;
        r += (int64_t)gridDim.x * blockDim.x) {
-    const long long deg = rowptr[r + 1] - rowptr[r];
-    mx = deg > mx ? deg : mx;
-    flag[r] = (split_len > 0 && deg > split_len) ? 1 : 0;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    long long u = __shfl_xor_sync(0xffffffffu, mx, o);
-    mx = u > mx ? u : mx;
-  }
-  if (lane_id() == 0 && mx > 0) atomicMax((long long*)&info[1], mx);
-}
-
-// pos = exclusive scan of flag. Compacts heavy rows and their chunk counts.
-__global__ void heavy_compact_kernel(const int64_t* __restrict__ rowptr,
-                                     const int32_t* __restrict__ flag,
-                                     const int32_t* __restrict__ pos, int64_t N, int64_t split_len,
-                                     int32_t* __restrict__ hrow, int64_t* __restrict__ hcnt,
-                                     int64_t* __restrict__ info) {
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < N;
-       r += (int64_t)gridDim.x * blockDim.x) {
-    const int f = flag[r];
-    if (f) {
-      const int64_t deg = rowptr[r + 1] - rowptr[r];
-      hrow[pos[r]] = (int32_t)r;
-      hcnt[pos[r]] = (deg + split_len - 1) / split_len;
+    const int64_t kb = rowptr[r], ke = rowptr[r + 1];
+    const bool empty = (ke == kb);
+    const bool span = !empty && (kb / chunk_len != (ke - 1) / chunk_len);
+    if (MODE == 0) {
+      mx = (ke - kb) > mx ? (ke - kb) : mx;
+      n_span += span;
+      n_empty += empty;
+    } else {
+      span_flag[r] = span;
+      empty_flag[r] = empty;
     }
-    if (r == N - 1) info[2] = (int64_t)pos[r] + f;
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      long long u = __shfl_xor_sync(0xffffffffu, mx, o);
+      mx = u > mx ? u : mx;
+    }
+    n_span = __reduce_add_sync(0xffffffffu, n_span);
+    n_empty = __reduce_add_sync(0xffffffffu, n_empty);
+    if (lane_id() == 0) {
+      if (mx > 0) atomicMax((long long*)&info[1], mx);
+      if (n_span) atomicAdd((unsigned long long*)&info[2], (unsigned long long)n_span);
+      if (n_empty) atomicAdd((unsigned long long*)&info[3], (unsigned long long)n_empty);
+    }
   }
 }
 
-__global__ void heavy_total_kernel(const int64_t* __restrict__ hcptr, int64_t* __restrict__ info) {
-  info[3] = hcptr[info[2]];
+__global__ void row_compact_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ pos,
+                                   int64_t N, int32_t* __restrict__ list) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < N;
+       r += (int64_t)gridDim.x * blockDim.x)
+    if (flag[r]) list[pos[r]] = (int32_t)r;
 }
 
-// Shared by plan_build and plan_from_rowptr. info[1..3], hrow, hcptr.
-static int heavy_analysis(const int64_t* rowptr, int64_t N, int64_t E_cap, int64_t split_len,
-                          int64_t* info, int32_t* hrow, int64_t* hcptr, Workspace& ws,
-                          cudaStream_t s) {
-  const int64_t n1 = N > 0 ? N : 1;
-  int32_t* flag = ws.take<int32_t>((size_t)n1);
-  int32_t* pos = ws.take<int32_t>((size_t)n1);
-  int32_t* scan_ws = ws.take<int32_t>(scan_workspace_elems(n1));
-  const int64_t cap = gno_plan_heavy_capacity(E_cap, split_len);
-  int64_t* scan_ws64 = ws.take<int64_t>(scan_workspace_elems(cap + 1));
-  if (!ws.ok()) return fail(GNO_ERR_WORKSPACE, "plan: workspace too small (%zu < %zu)", ws.size, ws.off);
-  GNO_CUDA(cudaMemsetAsync(hcptr, 0, (size_t)(cap + 1) * sizeof(int64_t), s));
-  if (N == 0) return GNO_OK;
-  heavy_flag_kernel<<<grid_for(N), 256, 0, s>>>(rowptr, flag, N, split_len, info);
-  GNO_LAUNCHED("heavy_flag_kernel");
-  int rc = exclusive_scan_i32(flag, pos, N, scan_ws, s);
-  if (rc) return rc;
-  heavy_compact_kernel<<<grid_for(N), 256, 0, s>>>(rowptr, flag, pos, N, split_len, hrow, hcptr, info);
-  GNO_LAUNCHED("heavy_compact_kernel");
-  rc = exclusive_scan_i64(hcptr, hcptr, cap + 1, scan_ws64, s);
-  if (rc) return rc;
-  heavy_total_kernel<<<1, 1, 0, s>>>(hcptr, info);
-  GNO_LAUNCHED("heavy_total_kernel");
-  return GNO_OK;
-}
-
-template <typename W>
-static void heavy_ws_layout(W& ws, int64_t N, int64_t E_cap, int64_t split_len_min) {
-  const int64_t n1 = N > 0 ? N : 1;
-  ws.template take<int32_t>((size_t)n1);
-  ws.template take<int32_t>((size_t)n1);
-  ws.template take<int32_t>(scan_workspace_elems(n1));
-  // capacity is largest for the smallest split_len the caller may use (>= 32)
-  ws.template take<int64_t>(scan_workspace_elems(E_cap / split_len_min + 2));
+// erow[k] = row containing sorted position k (binary search in rowptr).
+__global__ void expand_rows_kernel(const int64_t* __restrict__ rowptr, int64_t N, int64_t E,
+                                   int32_t* __restrict__ erow) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < E;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lo = 0, hi = N;  // largest r with rowptr[r] <= k
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (rowptr[mid] <= k) lo = mid; else hi = mid;
+    }
+    erow[k] = (int32_t)lo;
+  }
 }
 
 __global__ void permute_i64_to_i32_kernel(const int64_t* __restrict__ src,
@@ -154,39 +140,31 @@ using namespace gno;
 
 extern "C" {
 
-int64_t gno_plan_heavy_capacity(int64_t E, int64_t split_len) {
-  if (split_len <= 0) return 1;
-  return E / split_len + 1;
-}
-
 int gno_plan_workspace(int64_t E, int64_t N, size_t* bytes) {
   GNO_CHECK_ARG(bytes != nullptr, "gno_plan_workspace: bytes is NULL");
   GNO_CHECK_ARG(E >= 0 && E < (int64_t(1) << 31) && N >= 0 && N < (int64_t(1) << 31) - 1,
                 "gno_plan: E=%lld, N=%lld must be < 2^31", (long long)E, (long long)N);
+  (void)N;
   WorkspaceSizer sz;
   const int64_t e1 = E > 0 ? E : 1;
   sz.take<uint32_t>((size_t)e1);  // narrowed keys
-  sz.take<uint32_t>((size_t)e1);  // sorted keys
   sz.take<char>(sort_pairs_workspace(e1, 4, 4));
-  heavy_ws_layout(sz, N, e1, 32);
   *bytes = sz.total();
   return GNO_OK;
 }
 
-int gno_plan_build(const int64_t* index, int64_t E, int64_t N, int64_t split_len, int64_t* rowptr,
-                   int32_t* perm, int64_t* info, int32_t* hrow, int64_t* hcptr, void* wsp,
-                   size_t ws_bytes, gno_stream_t stream) {
+int gno_plan_build(const int64_t* index, int64_t E, int64_t N, int64_t chunk_len, int64_t* rowptr,
+                   int32_t* perm, int32_t* erow, int64_t* info, void* wsp, size_t ws_bytes,
+                   gno_stream_t stream) {
   cudaStream_t s = (cudaStream_t)stream;
   GNO_CHECK_ARG(E >= 0 && E < (int64_t(1) << 31) && N >= 0 && N < (int64_t(1) << 31) - 1,
                 "gno_plan_build: E=%lld, N=%lld must be < 2^31", (long long)E, (long long)N);
-  GNO_CHECK_ARG(split_len == 0 || split_len >= 32, "gno_plan_build: split_len must be 0 or >= 32");
-  GNO_CHECK_ARG(rowptr && info && hrow && hcptr && (E == 0 || (index && perm)),
-                "gno_plan_build: NULL buffer");
+  GNO_CHECK_ARG(chunk_len >= 32 && chunk_len % 32 == 0, "gno_plan_build: chunk_len must be a multiple of 32");
+  GNO_CHECK_ARG(rowptr && info && (E == 0 || (index && perm && erow)), "gno_plan_build: NULL buffer");
   if (wsp == nullptr) return fail(GNO_ERR_WORKSPACE, "gno_plan_build: workspace is NULL");
   Workspace ws(wsp, ws_bytes);
   const int64_t e1 = E > 0 ? E : 1;
   uint32_t* keys = ws.take<uint32_t>((size_t)e1);
-  uint32_t* keys_sorted = ws.take<uint32_t>((size_t)e1);
   const size_t sort_bytes = sort_pairs_workspace(e1, 4, 4);
   char* sort_ws = ws.take<char>(sort_bytes);
   if (!ws.ok()) return fail(GNO_ERR_WORKSPACE, "gno_plan_build: workspace too small (%zu < %zu)", ws_bytes, ws.off);
@@ -194,36 +172,77 @@ int gno_plan_build(const int64_t* index, int64_t E, int64_t N, int64_t split_len
   if (E > 0) {
     narrow_keys_kernel<<<grid_for(E), 256, 0, s>>>(index, keys, E, N, info);
     GNO_LAUNCHED("narrow_keys_kernel");
-    int rc = sort_pairs(keys, keys_sorted, nullptr, perm, E, 4, 4, 0, bits_for(N), sort_ws,
-                        sort_bytes, s);
+    int rc = sort_pairs(keys, erow, nullptr, perm, E, 4, 4, 0, bits_for(N), sort_ws, sort_bytes, s);
     if (rc) return rc;
   }
-  rowptr_kernel<<<grid_for(E + 1), 256, 0, s>>>(keys_sorted, rowptr, E, N);
+  rowptr_kernel<<<grid_for(E + 1), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(erow), rowptr, E, N);
   GNO_LAUNCHED("rowptr_kernel");
-  return heavy_analysis(rowptr, N, e1, split_len, info, hrow, hcptr, ws, s);
+  if (N > 0) {
+    row_class_kernel<0><<<grid_for(N), 256, 0, s>>>(rowptr, N, chunk_len, nullptr, nullptr, info);
+    GNO_LAUNCHED("row_class_kernel");
+  }
+  return GNO_OK;
 }
 
-int gno_plan_from_rowptr_workspace(int64_t N, int64_t E, size_t* bytes) {
-  GNO_CHECK_ARG(bytes != nullptr, "gno_plan_from_rowptr_workspace: bytes is NULL");
-  GNO_CHECK_ARG(E >= 0 && N >= 0, "gno_plan_from_rowptr_workspace: negative size");
+int gno_plan_from_rowptr(const int64_t* rowptr, int64_t N, int64_t E, int64_t chunk_len,
+                         int32_t* erow, int64_t* info, gno_stream_t stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  GNO_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31) - 1 && E >= 0 && E < (int64_t(1) << 31),
+                "gno_plan_from_rowptr: N=%lld, E=%lld must be < 2^31", (long long)N, (long long)E);
+  GNO_CHECK_ARG(chunk_len >= 32 && chunk_len % 32 == 0, "gno_plan_from_rowptr: chunk_len must be a multiple of 32");
+  GNO_CHECK_ARG(rowptr && info && (E == 0 || erow), "gno_plan_from_rowptr: NULL buffer");
+  GNO_CUDA(cudaMemsetAsync(info, 0, 4 * sizeof(int64_t), s));
+  if (E > 0 && N > 0) {
+    expand_rows_kernel<<<grid_for(E), 256, 0, s>>>(rowptr, N, E, erow);
+    GNO_LAUNCHED("expand_rows_kernel");
+  }
+  if (N > 0) {
+    row_class_kernel<0><<<grid_for(N), 256, 0, s>>>(rowptr, N, chunk_len, nullptr, nullptr, info);
+    GNO_LAUNCHED("row_class_kernel");
+  }
+  return GNO_OK;
+}
+
+int gno_plan_lists_workspace(int64_t N, size_t* bytes) {
+  GNO_CHECK_ARG(bytes != nullptr && N >= 0, "gno_plan_lists_workspace: bad argument");
   WorkspaceSizer sz;
-  heavy_ws_layout(sz, N, E > 0 ? E : 1, 32);
+  const int64_t n1 = N > 0 ? N : 1;
+  for (int i = 0; i < 4; ++i) sz.take<int32_t>((size_t)n1);
+  sz.take<int32_t>(scan_workspace_elems(n1));
   *bytes = sz.total();
   return GNO_OK;
 }
 
-int gno_plan_from_rowptr(const int64_t* rowptr, int64_t N, int64_t E, int64_t split_len, int64_t* info,
-                         int32_t* hrow, int64_t* hcptr, void* wsp, size_t ws_bytes,
-                         gno_stream_t stream) {
+int gno_plan_lists(const int64_t* rowptr, int64_t N, int64_t chunk_len, int32_t* srow,
+                   int32_t* zrow, void* wsp, size_t ws_bytes, gno_stream_t stream) {
   cudaStream_t s = (cudaStream_t)stream;
-  GNO_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31) - 1 && E >= 0 && E < (int64_t(1) << 31),
-                "gno_plan_from_rowptr: N=%lld, E=%lld must be < 2^31", (long long)N, (long long)E);
-  GNO_CHECK_ARG(split_len == 0 || split_len >= 32, "gno_plan_from_rowptr: split_len must be 0 or >= 32");
-  GNO_CHECK_ARG(rowptr && info && hrow && hcptr, "gno_plan_from_rowptr: NULL buffer");
-  if (wsp == nullptr) return fail(GNO_ERR_WORKSPACE, "gno_plan_from_rowptr: workspace is NULL");
+  GNO_CHECK_ARG(N >= 0 && N < (int64_t(1) << 31) - 1, "gno_plan_lists: N=%lld must be < 2^31", (long long)N);
+  GNO_CHECK_ARG(chunk_len >= 32 && chunk_len % 32 == 0, "gno_plan_lists: chunk_len must be a multiple of 32");
+  if (N == 0) return GNO_OK;
+  GNO_CHECK_ARG(rowptr != nullptr, "gno_plan_lists: rowptr is NULL");
+  if (wsp == nullptr) return fail(GNO_ERR_WORKSPACE, "gno_plan_lists: workspace is NULL");
   Workspace ws(wsp, ws_bytes);
-  GNO_CUDA(cudaMemsetAsync(info, 0, 4 * sizeof(int64_t), s));
-  return heavy_analysis(rowptr, N, E > 0 ? E : 1, split_len, info, hrow, hcptr, ws, s);
+  int32_t* span_flag = ws.take<int32_t>((size_t)N);
+  int32_t* empty_flag = ws.take<int32_t>((size_t)N);
+  int32_t* span_pos = ws.take<int32_t>((size_t)N);
+  int32_t* empty_pos = ws.take<int32_t>((size_t)N);
+  int32_t* scan_ws = ws.take<int32_t>(scan_workspace_elems(N));
+  if (!ws.ok()) return fail(GNO_ERR_WORKSPACE, "gno_plan_lists: workspace too small (%zu < %zu)", ws_bytes, ws.off);
+  row_class_kernel<1><<<grid_for(N), 256, 0, s>>>(rowptr, N, chunk_len, span_flag, empty_flag, nullptr);
+  GNO_LAUNCHED("row_class_kernel");
+  int rc = exclusive_scan_i32(span_flag, span_pos, N, scan_ws, s);
+  if (rc) return rc;
+  rc = exclusive_scan_i32(empty_flag, empty_pos, N, scan_ws, s);
+  if (rc) return rc;
+  if (srow) {
+    row_compact_kernel<<<grid_for(N), 256, 0, s>>>(span_flag, span_pos, N, srow);
+    GNO_LAUNCHED("row_compact_kernel");
+  }
+  if (zrow) {
+    row_compact_kernel<<<grid_for(N), 256, 0, s>>>(empty_flag, empty_pos, N, zrow);
+    GNO_LAUNCHED("row_compact_kernel");
+  }
+  return GNO_OK;
 }
 
 int gno_permute_i64_to_i32(const int64_t* src, const int32_t* perm, int32_t* out, int64_t E,

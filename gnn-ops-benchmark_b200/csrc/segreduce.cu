@@ -1,50 +1,56 @@
-// Segment reduce over a dst-sorted CSR: the hot kernel of the path.
+// Segment reduce over a dst-sorted edge list: the hot kernel of the path.
 //
-//   out[i, :] = reduce_{k in [rowptr[i], rowptr[i+1])}  w[k] * x[gidx[k], :]
+//   out[i, :] = reduce_{k : erow[k] = i}  w[k] * x[gidx[k], :]
 //
-// Work item = (destination row, 32-vector column tile) → one warp.  A warp
-// loads 32 sorted-edge indices with one coalesced request, broadcasts them by
-// shuffle, and gathers the feature rows with VB-byte vector loads (16/8/4/2
-// chosen from the row alignment), U independent rows in flight per lane.
-// Rows narrower than 32 vectors are processed P = 32/G edges at a time by G-lane
-// groups and combined by shuffle.  Rows longer than split_len are cut into
-// fixed chunks whose partials (fp32 + arg) are combined in chunk order by a
-// second kernel — no atomics anywhere, so results are bit-reproducible, and
-// arg ties resolve to the lowest original edge position exactly like the
-// sequential upstream CPU loop.
+// EDGE-BALANCED segmented reduction.  The sorted edge list is cut into chunks
+// of chunk_len edges; a worker (a group of G lanes, G*VB bytes >= one feature
+// row, or a full warp per 32-vector column tile for wide rows) owns one chunk,
+// so every worker moves the same number of bytes no matter how skewed the
+// degrees are (power-law graphs need no special case).  A worker stages G
+// sorted-edge records (gather index, destination row, edge id, weight) in its
+// lanes with one coalesced request per array, broadcasts them by shuffle,
+// keeps U independent VB-byte (16/8/4/2 by alignment) feature-row loads in
+// flight, and accumulates in fp32.  When the destination row changes it
+// writes the finished row; the rows cut by a chunk boundary go to a partial
+// buffer (two slots per chunk) and are combined IN CHUNK ORDER by
+// segfinish_kernel, which also zero-fills empty rows.  No atomics anywhere:
+// results are bit-reproducible, and MIN/MAX ties resolve to the lowest
+// original edge position exactly like the sequential upstream CPU loop.
 //
 // Roofline: HBM.  Algorithmic bytes per edge = F*s (feature row) + 4 (index)
-// [+4 eid for arg, +s weight]; per row = F*s_out [+8F arg] + 8 (rowptr).
+// [+4 erow, +4 eid for arg, +s weight]; per row = F*s_out [+8F arg].
 #include <climits>
 
 #include "common.cuh"
 
 namespace gno {
 
-constexpr int kSegThreads = 256;
+constexpr int kSegThreads = 128;
 constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kNoArg = INT_MAX;
 
 struct SegParams {
-  const int64_t* rowptr;
   const int32_t* gidx;
   const int32_t* eid;
+  const int32_t* erow;
   const void* x;
   const void* w;
   void* out;
   int64_t* arg;
-  float* part_val;    // [n_chunks, F] fp32 partials of split rows
-  int32_t* part_arg;  // [n_chunks, F]
-  const int32_t* hrow;
-  const int64_t* hcptr;
-  int64_t N, n_heavy, n_chunks, split_len;
+  float* part_val;    // [2 * n_chunks, F] fp32 partials of rows cut by a chunk boundary
+  int32_t* part_arg;  // [2 * n_chunks, F]
+  const int64_t* rowptr;
+  const int32_t* srow;
+  const int32_t* zrow;
+  int64_t N, E, n_chunks, n_span, n_empty;
   int64_t F;
   int64_t ldx_bytes, ldo_bytes;
   int64_t arg_fill;
-  int nvec;      // vectors per row
-  int ncoltiles; // column tiles of 32 vectors
-  int G;         // lanes per edge group (power of two; 32 when ncoltiles > 1)
-  int mean;      // divide by max(row length, 1)
+  int chunk_len;  // edges per worker
+  int nvec;       // vectors per row
+  int ncoltiles;  // column tiles of 32 vectors
+  int G;          // lanes per worker (power of two; 32 when ncoltiles > 1)
+  int mean;       // divide by max(row length, 1)
   int accumulate;
 };
 
@@ -161,150 +167,30 @@ __device__ __forceinline__ float finalize(float a, int e, float prev, float cnt,
   return a;
 }
 
-template <typename T, int VB, int RED, bool ARG, bool HAS_W, int U>
-__global__ void __launch_bounds__(kSegThreads) segreduce_kernel(const SegParams p) {
+// Write one finished (or partial) row segment held by a worker.
+template <typename T, int VB, int RED, bool ARG>
+__device__ __forceinline__ void flush_row(const SegParams& p, int64_t row, int64_t chunk, bool head,
+                                          bool tail, int64_t seg_len, int v,
+                                          const float (&acc)[VB / (int)sizeof(T)],
+                                          const int (&ae)[ARG ? VB / (int)sizeof(T) : 1]) {
   constexpr int EPV = VB / (int)sizeof(T);
-  const int lane = threadIdx.x & 31;
-  const int64_t wid = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5);
-  const int64_t n_light = p.N * p.ncoltiles;
-
-  int64_t row, kbeg, kend, chunk = -1;
-  int ct;
-  if (wid < n_light) {
-    row = wid / p.ncoltiles;
-    ct = (int)(wid - row * p.ncoltiles);
-    kbeg = p.rowptr[row];
-    kend = p.rowptr[row + 1];
-    if (p.split_len > 0 && kend - kbeg > p.split_len) return;  // split rows: chunk items below
-  } else {
-    const int64_t hw = wid - n_light;
-    chunk = hw / p.ncoltiles;
-    ct = (int)(hw - chunk * p.ncoltiles);
-    if (chunk >= p.n_chunks) return;
-    // largest h with hcptr[h] <= chunk
-    int64_t lo = 0, hi = p.n_heavy;
-    while (hi - lo > 1) {
-      const int64_t mid = (lo + hi) >> 1;
-      if (p.hcptr[mid] <= chunk) lo = mid; else hi = mid;
-    }
-    row = p.hrow[lo];
-    kbeg = p.rowptr[row] + (chunk - p.hcptr[lo]) * p.split_len;
-    kend = min(kbeg + p.split_len, p.rowptr[row + 1]);
-  }
-
-  const int G = p.G;
-  const int P = 32 / G;
-  const int grp = lane / G;
-  const int v = ct * 32 + (lane & (G - 1));
-  const bool vact = v < p.nvec;
-  const char* xcol = static_cast<const char*>(p.x) + (int64_t)v * VB;
-
-  float acc[EPV];
-  int ae[ARG ? EPV : 1];
-#pragma unroll
-  for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
-  if constexpr (ARG) {
-#pragma unroll
-    for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
-  }
-
-  const bool stream_idx = (p.ncoltiles == 1);
-  const uint64_t pol_stream = l2_policy_evict_first();
-  for (int64_t kb = kbeg; kb < kend; kb += 32) {
-    const int cnt = (int)gno::imin64(32, kend - kb);
-    int my_idx = 0, my_e = 0;
-    float my_w = 0.f;
-    if (lane < cnt) {
-      const int64_t k = kb + lane;
-      if (p.gidx)
-        my_idx = stream_idx ? ld_stream_i32(p.gidx + k, pol_stream) : __ldg(p.gidx + k);
-      else
-        my_idx = (int)k;
-      if constexpr (ARG) {
-        if (p.eid == p.gidx)
-          my_e = my_idx;
-        else if (p.eid)
-          my_e = stream_idx ? ld_stream_i32(p.eid + k, pol_stream) : __ldg(p.eid + k);
-        else
-          my_e = (int)k;
-      }
-      if constexpr (HAS_W) my_w = DType<T>::to_f(static_cast<const T*>(p.w)[k]);
-    }
-    for (int j = 0; j < cnt; j += P * U) {
-      Words<VB> val[U];
-      int e_u[ARG ? U : 1];
-      float w_u[HAS_W ? U : 1];
-      bool ok[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int slot = j + u * P + grp;
-        const int idx = __shfl_sync(0xffffffffu, my_idx, slot & 31);
-        if constexpr (ARG) e_u[u] = __shfl_sync(0xffffffffu, my_e, slot & 31);
-        if constexpr (HAS_W) w_u[u] = __shfl_sync(0xffffffffu, my_w, slot & 31);
-        ok[u] = vact && (slot < cnt);
-        if (ok[u]) val[u] = ld_vec<VB>(xcol + (int64_t)idx * p.ldx_bytes);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (ok[u]) {
-#pragma unroll
-          for (int i = 0; i < EPV; ++i) {
-            const float f = elem<T, VB>(val[u], i);
-            if constexpr (RED == GNO_SUM) {
-              if constexpr (HAS_W) acc[i] = fmaf(w_u[u], f, acc[i]);
-              else acc[i] += f;
-            } else if constexpr (RED == GNO_MUL) {
-              acc[i] *= f;
-            } else {
-              if (better<RED>(f, acc[i])) {
-                acc[i] = f;
-                if constexpr (ARG) ae[i] = e_u[u];
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-
-  // Combine the P edge groups (fixed butterfly order → deterministic).
-  for (int o = G; o < 32; o <<= 1) {
-#pragma unroll
-    for (int i = 0; i < EPV; ++i) {
-      const float ov = __shfl_xor_sync(0xffffffffu, acc[i], o);
-      if constexpr (RED == GNO_SUM) {
-        acc[i] += ov;
-      } else if constexpr (RED == GNO_MUL) {
-        acc[i] *= ov;
-      } else if constexpr (ARG) {
-        const int oe = __shfl_xor_sync(0xffffffffu, ae[i], o);
-        if (better<RED>(ov, acc[i]) || (ov == acc[i] && oe < ae[i])) {
-          acc[i] = ov;
-          ae[i] = oe;
-        }
-      } else {
-        if (better<RED>(ov, acc[i])) acc[i] = ov;
-      }
-    }
-  }
-  if (grp != 0 || !vact) return;
-
-  if (chunk >= 0) {  // split row: fp32 partial (+arg) for the combine kernel
-    float* pv = p.part_val + chunk * p.F + (int64_t)v * EPV;
+  if (head || tail) {
+    // a chunk that lies entirely inside one row is both: it uses the head slot
+    const int64_t slot = 2 * chunk + (head ? 0 : 1);
+    float* pv = p.part_val + slot * p.F + (int64_t)v * EPV;
 #pragma unroll
     for (int i = 0; i < EPV; ++i) pv[i] = acc[i];
     if constexpr (ARG) {
-      int32_t* pa = p.part_arg + chunk * p.F + (int64_t)v * EPV;
+      int32_t* pa = p.part_arg + slot * p.F + (int64_t)v * EPV;
 #pragma unroll
       for (int i = 0; i < EPV; ++i) pa[i] = ae[i];
     }
     return;
   }
-
   char* optr = static_cast<char*>(p.out) + row * p.ldo_bytes + (int64_t)v * VB;
   Words<VB> prev;
   if (p.accumulate) prev = ld_vec<VB>(optr);
-  const float cnt = p.mean ? (float)gno::imax64(kend - kbeg, 1) : 0.f;
+  const float cnt = p.mean ? (float)imax64(seg_len, 1) : 0.f;
   Words<VB> o;
 #pragma unroll
   for (int i = 0; i < EPV; ++i) {
@@ -320,89 +206,223 @@ __global__ void __launch_bounds__(kSegThreads) segreduce_kernel(const SegParams 
   st_vec<VB>(optr, o);
 }
 
-// Combine the chunk partials of split rows in chunk order: one thread per
-// (heavy row, feature).
-template <typename T, int RED, bool ARG>
-__global__ void __launch_bounds__(256) segcombine_kernel(const SegParams p) {
-  const int64_t total = p.n_heavy * p.F;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t h = i / p.F, f = i - h * p.F;
-    const int64_t row = p.hrow[h];
-    float a = red_init<T, RED>();
-    int e = kNoArg;
-    for (int64_t c = p.hcptr[h]; c < p.hcptr[h + 1]; ++c) {
-      const float pv = p.part_val[c * p.F + f];
-      if constexpr (RED == GNO_SUM) {
-        a += pv;
-      } else if constexpr (RED == GNO_MUL) {
-        a *= pv;
-      } else {
-        // chunks ascend in edge position, so strict compare keeps the lowest
-        if (better<RED>(pv, a)) {
-          a = pv;
-          if constexpr (ARG) e = p.part_arg[c * p.F + f];
+template <typename T, int VB, int RED, bool ARG, bool HAS_W, int U>
+__global__ void __launch_bounds__(kSegThreads) segreduce_kernel(const SegParams p) {
+  constexpr int EPV = VB / (int)sizeof(T);
+  const int lane = threadIdx.x & 31;
+  const int G = p.G;
+  const int grp = lane / G;       // worker within the warp
+  const int li = lane & (G - 1);  // lane within the worker
+  const int gbase = lane - li;
+  const int64_t warp = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5);
+  const int64_t wk = warp * (32 / G) + grp;
+  const int64_t chunk = wk / p.ncoltiles;
+  const int ct = (int)(wk - chunk * p.ncoltiles);
+  const int C = p.chunk_len;
+  const bool active = chunk < p.n_chunks;
+  const int64_t k0 = chunk * C;
+  const int64_t k1 = active ? imin64(k0 + C, p.E) : k0;
+  const int v = ct * 32 + li;
+  const bool vact = active && (v < p.nvec);
+  const char* xcol = static_cast<const char*>(p.x) + (int64_t)v * VB;
+  const bool stream_idx = (p.ncoltiles == 1);
+  const uint64_t pol_stream = l2_policy_evict_first();
+
+  float acc[EPV];
+  int ae[ARG ? EPV : 1];
+#pragma unroll
+  for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
+  if constexpr (ARG) {
+#pragma unroll
+    for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
+  }
+  int cur_row = active ? __ldg(p.erow + k0) : 0;
+  bool head = active && k0 > 0 && __ldg(p.erow + k0 - 1) == cur_row;
+  int64_t seg_start = k0;
+
+  for (int t = 0; t < C; t += G) {
+    // stage G edge records in the worker's lanes (coalesced)
+    const int64_t k = k0 + t + li;
+    int my_idx = 0, my_row = 0, my_e = 0;
+    float my_w = 0.f;
+    if (k < k1) {
+      my_row = stream_idx ? ld_stream_i32(p.erow + k, pol_stream) : __ldg(p.erow + k);
+      if (p.gidx)
+        my_idx = stream_idx ? ld_stream_i32(p.gidx + k, pol_stream) : __ldg(p.gidx + k);
+      else
+        my_idx = (int)k;
+      if constexpr (ARG) {
+        if (p.eid == p.gidx)
+          my_e = my_idx;
+        else if (p.eid)
+          my_e = stream_idx ? ld_stream_i32(p.eid + k, pol_stream) : __ldg(p.eid + k);
+        else
+          my_e = (int)k;
+      }
+      if constexpr (HAS_W) my_w = DType<T>::to_f(static_cast<const T*>(p.w)[k]);
+    }
+    for (int j = 0; j < G; j += U) {
+      Words<VB> val[U];
+      int row_u[U];
+      int e_u[ARG ? U : 1];
+      float w_u[HAS_W ? U : 1];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int slot = j + u;
+        const int src_lane = gbase + (slot & (G - 1));
+        const int idx = __shfl_sync(0xffffffffu, my_idx, src_lane);
+        row_u[u] = __shfl_sync(0xffffffffu, my_row, src_lane);
+        if constexpr (ARG) e_u[u] = __shfl_sync(0xffffffffu, my_e, src_lane);
+        if constexpr (HAS_W) w_u[u] = __shfl_sync(0xffffffffu, my_w, src_lane);
+        ok[u] = (slot < G) && (k0 + t + slot < k1);
+        if (ok[u] && vact) val[u] = ld_vec<VB>(xcol + (int64_t)idx * p.ldx_bytes);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (ok[u]) {
+          if (row_u[u] != cur_row) {  // the previous row ended inside this chunk
+            const int64_t kk = k0 + t + j + u;
+            if (vact) flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, false, kk - seg_start, v, acc, ae);
+            head = false;
+            cur_row = row_u[u];
+            seg_start = kk;
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
+            if constexpr (ARG) {
+#pragma unroll
+              for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
+            }
+          }
+          if (vact) {
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) {
+              const float f = elem<T, VB>(val[u], i);
+              if constexpr (RED == GNO_SUM) {
+                if constexpr (HAS_W) acc[i] = fmaf(w_u[u], f, acc[i]);
+                else acc[i] += f;
+              } else if constexpr (RED == GNO_MUL) {
+                acc[i] *= f;
+              } else {
+                if (better<RED>(f, acc[i])) {
+                  acc[i] = f;
+                  if constexpr (ARG) ae[i] = e_u[u];
+                }
+              }
+            }
+          }
         }
       }
     }
-    T* op = reinterpret_cast<T*>(static_cast<char*>(p.out) + row * p.ldo_bytes) + f;
-    const float prev = p.accumulate ? DType<T>::to_f(*op) : 0.f;
-    float cnt = 0.f;
-    if (p.mean) cnt = (float)gno::imax64(p.rowptr[row + 1] - p.rowptr[row], 1);
-    const float r = finalize<T, RED>(a, e, prev, cnt, p.accumulate, p.arg_fill,
-                                     (ARG && p.arg) ? p.arg + row * p.F + f : nullptr);
-    *op = DType<T>::from_f(r);
+  }
+  if (vact && k1 > k0) {
+    const bool tail = (k1 < p.E) && (__ldg(p.erow + k1) == cur_row);
+    flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, tail, k1 - seg_start, v, acc, ae);
+  }
+}
+
+// Finish pass: (a) rows cut by a chunk boundary — combine their partials in
+// chunk order: the tail slot of the first chunk, then the head slot of every
+// later chunk; (b) empty rows — write zeros (and arg_fill).  One thread per
+// (row, feature).
+template <typename T, int RED, bool ARG>
+__global__ void __launch_bounds__(256) segfinish_kernel(const SegParams p) {
+  const int64_t n_a = p.n_span * p.F;
+  const int64_t total = n_a + (p.accumulate ? 0 : p.n_empty * p.F);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < n_a) {
+      const int64_t s = i / p.F, f = i - s * p.F;
+      const int64_t row = p.srow[s];
+      const int64_t kb = p.rowptr[row], ke = p.rowptr[row + 1];
+      const int64_t ca = kb / p.chunk_len, cb = (ke - 1) / p.chunk_len;
+      float a = p.part_val[(2 * ca + 1) * p.F + f];
+      int e = kNoArg;
+      if constexpr (ARG) e = p.part_arg[(2 * ca + 1) * p.F + f];
+      for (int64_t c = ca + 1; c <= cb; ++c) {
+        const float pv = p.part_val[(2 * c) * p.F + f];
+        if constexpr (RED == GNO_SUM) {
+          a += pv;
+        } else if constexpr (RED == GNO_MUL) {
+          a *= pv;
+        } else {
+          // chunks ascend in edge position, so a strict compare keeps the lowest
+          if (better<RED>(pv, a)) {
+            a = pv;
+            if constexpr (ARG) e = p.part_arg[(2 * c) * p.F + f];
+          }
+        }
+      }
+      T* op = reinterpret_cast<T*>(static_cast<char*>(p.out) + row * p.ldo_bytes) + f;
+      const float prev = p.accumulate ? DType<T>::to_f(*op) : 0.f;
+      const float cnt = p.mean ? (float)imax64(ke - kb, 1) : 0.f;
+      const float r = finalize<T, RED>(a, e, prev, cnt, p.accumulate, p.arg_fill,
+                                       (ARG && p.arg) ? p.arg + row * p.F + f : nullptr);
+      *op = DType<T>::from_f(r);
+    } else {
+      const int64_t j = i - n_a;
+      const int64_t z = j / p.F, f = j - z * p.F;
+      const int64_t row = p.zrow[z];
+      T* op = reinterpret_cast<T*>(static_cast<char*>(p.out) + row * p.ldo_bytes) + f;
+      // torch_scatter: empty rows are 0 for sum/mean/min/max and 1 for mul
+      *op = DType<T>::from_f(RED == GNO_MUL ? 1.f : 0.f);
+      if constexpr (ARG) {
+        if (p.arg) p.arg[row * p.F + f] = p.arg_fill;
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------- dispatch --
 template <typename T, int VB, int RED, bool ARG, bool HAS_W>
-static int launch_seg(const SegParams& p, int64_t warps, cudaStream_t s) {
+static int launch_seg(const SegParams& p, cudaStream_t s) {
   constexpr int U = VB >= 16 ? 8 : 16;
+  const int64_t workers = p.n_chunks * p.ncoltiles;
+  const int64_t warps = ceil_div(workers, 32 / p.G);
   const int64_t blocks = ceil_div(warps, kSegWarps);
   if (blocks > 0) {
     segreduce_kernel<T, VB, RED, ARG, HAS_W, U><<<(unsigned)blocks, kSegThreads, 0, s>>>(p);
     GNO_LAUNCHED("segreduce_kernel");
   }
-  if (p.n_heavy > 0) {
-    const int64_t total = p.n_heavy * p.F;
-    const int grid = (int)gno::imin64(ceil_div(total, 256), (int64_t)kNumSMs * 16);
-    segcombine_kernel<T, RED, ARG><<<grid, 256, 0, s>>>(p);
-    GNO_LAUNCHED("segcombine_kernel");
+  const int64_t total = p.n_span * p.F + (p.accumulate ? 0 : p.n_empty * p.F);
+  if (total > 0) {
+    const int grid = (int)imin64(ceil_div(total, 256), (int64_t)kNumSMs * 16);
+    segfinish_kernel<T, RED, ARG><<<grid, 256, 0, s>>>(p);
+    GNO_LAUNCHED("segfinish_kernel");
   }
   return GNO_OK;
 }
 
 template <typename T, int VB>
 static int dispatch_red(const SegParams& p, int reduce, bool /*with_arg*/, bool has_w,
-                        int64_t warps, cudaStream_t s) {
+                        cudaStream_t s) {
   switch (reduce) {
     case GNO_SUM:
     case GNO_MEAN:
-      return has_w ? launch_seg<T, VB, GNO_SUM, false, true>(p, warps, s)
-                   : launch_seg<T, VB, GNO_SUM, false, false>(p, warps, s);
+      return has_w ? launch_seg<T, VB, GNO_SUM, false, true>(p, s)
+                   : launch_seg<T, VB, GNO_SUM, false, false>(p, s);
     case GNO_MUL:
-      return launch_seg<T, VB, GNO_MUL, false, false>(p, warps, s);
+      return launch_seg<T, VB, GNO_MUL, false, false>(p, s);
     // MIN/MAX always track the winner's position (even with arg == NULL) so
     // that ties between +0.0 and -0.0 resolve to the first occurrence, which
     // keeps the VALUES bit-identical to the sequential upstream loop.
     case GNO_MIN:
-      return launch_seg<T, VB, GNO_MIN, true, false>(p, warps, s);
+      return launch_seg<T, VB, GNO_MIN, true, false>(p, s);
     case GNO_MAX:
-      return launch_seg<T, VB, GNO_MAX, true, false>(p, warps, s);
+      return launch_seg<T, VB, GNO_MAX, true, false>(p, s);
   }
   return fail(GNO_ERR_INVALID, "gno_segment_reduce: unknown reduce %d", reduce);
 }
 
 template <typename T>
 static int dispatch_vb(const SegParams& p, int vb, int reduce, bool with_arg, bool has_w,
-                       int64_t warps, cudaStream_t s) {
+                       cudaStream_t s) {
   switch (vb) {
-    case 16: return dispatch_red<T, 16>(p, reduce, with_arg, has_w, warps, s);
-    case 8: return dispatch_red<T, 8>(p, reduce, with_arg, has_w, warps, s);
-    case 4: return dispatch_red<T, 4>(p, reduce, with_arg, has_w, warps, s);
+    case 16: return dispatch_red<T, 16>(p, reduce, with_arg, has_w, s);
+    case 8: return dispatch_red<T, 8>(p, reduce, with_arg, has_w, s);
+    case 4: return dispatch_red<T, 4>(p, reduce, with_arg, has_w, s);
     case 2:
-      if constexpr (sizeof(T) == 2) return dispatch_red<T, 2>(p, reduce, with_arg, has_w, warps, s);
+      if constexpr (sizeof(T) == 2) return dispatch_red<T, 2>(p, reduce, with_arg, has_w, s);
   }
   return fail(GNO_ERR_INVALID, "gno_segment_reduce: bad vector width %d", vb);
 }
@@ -418,12 +438,14 @@ extern "C" {
 int gno_segment_reduce_workspace(const gno_csr* g, int64_t F, int dtype, int reduce, int with_arg,
                                  size_t* bytes) {
   GNO_CHECK_ARG(g && bytes, "gno_segment_reduce_workspace: NULL argument");
+  GNO_CHECK_ARG(g->chunk_len >= 32 && g->chunk_len % 32 == 0, "gno_segment_reduce: bad chunk_len");
   (void)dtype;
+  (void)with_arg;
   WorkspaceSizer sz;
-  if (g->n_chunks > 0) {
-    sz.take<float>((size_t)(g->n_chunks * F));
-    if (with_arg || reduce == GNO_MIN || reduce == GNO_MAX)
-      sz.take<int32_t>((size_t)(g->n_chunks * F));
+  const int64_t n_chunks = ceil_div(g->E, g->chunk_len);
+  if (n_chunks > 0) {
+    sz.take<float>((size_t)(2 * n_chunks * F));
+    if (reduce == GNO_MIN || reduce == GNO_MAX) sz.take<int32_t>((size_t)(2 * n_chunks * F));
   }
   *bytes = sz.total();
   return GNO_OK;
@@ -438,12 +460,16 @@ int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows, int64_t 
   GNO_CHECK_ARG(dtype == GNO_F32 || dtype == GNO_F16 || dtype == GNO_BF16,
                 "gno_segment_reduce: unknown dtype %d", dtype);
   GNO_CHECK_ARG(reduce >= GNO_SUM && reduce <= GNO_MAX, "gno_segment_reduce: unknown reduce %d", reduce);
-  GNO_CHECK_ARG(g->N >= 0 && g->E >= 0 && F >= 0 && ldx >= F && ldo >= F,
+  GNO_CHECK_ARG(g->N >= 0 && g->E >= 0 && g->E < (int64_t(1) << 31) && F >= 0 && ldx >= F && ldo >= F,
                 "gno_segment_reduce: bad sizes N=%lld E=%lld F=%lld ldx=%lld ldo=%lld",
                 (long long)g->N, (long long)g->E, (long long)F, (long long)ldx, (long long)ldo);
+  GNO_CHECK_ARG(g->chunk_len >= 32 && g->chunk_len % 32 == 0 && g->chunk_len <= (1 << 20),
+                "gno_segment_reduce: chunk_len must be a multiple of 32");
   if (g->N == 0 || F == 0) return GNO_OK;
-  GNO_CHECK_ARG(g->rowptr && out && (x || g->E == 0), "gno_segment_reduce: NULL buffer");
+  GNO_CHECK_ARG(g->rowptr && out && (g->E == 0 || (x && g->erow)), "gno_segment_reduce: NULL buffer");
   GNO_CHECK_ARG(x_rows >= 0, "gno_segment_reduce: x_rows < 0");
+  GNO_CHECK_ARG((g->n_span == 0 || g->srow) && (g->n_empty == 0 || g->zrow),
+                "gno_segment_reduce: row lists missing");
   const bool with_arg = (arg != nullptr);
   GNO_CHECK_ARG(!with_arg || reduce == GNO_MIN || reduce == GNO_MAX,
                 "gno_segment_reduce: arg output only for MIN/MAX");
@@ -451,31 +477,33 @@ int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows, int64_t 
                 "gno_segment_reduce: accumulate only for SUM/MUL");
   if (w != nullptr && !(reduce == GNO_SUM || reduce == GNO_MEAN))
     return fail(GNO_ERR_UNSUPPORTED, "gno_segment_reduce: edge weights only with SUM/MEAN");
-  GNO_CHECK_ARG(g->n_heavy == 0 || (g->hrow && g->hcptr && g->split_len >= 32),
-                "gno_segment_reduce: split table missing");
 
   const int es = dtype_size(dtype);
+  GNO_CHECK_ARG((((uintptr_t)x | (uintptr_t)out) % es) == 0,
+                "gno_segment_reduce: buffers not aligned to the element size");
   // Widest vector every row start and the row length allow.
   const uintptr_t a = (uintptr_t)x | (uintptr_t)out | (uintptr_t)(ldx * es) | (uintptr_t)(ldo * es) |
                       (uintptr_t)(F * es);
   int vb = 16;
   while (vb > es && (a % vb) != 0) vb >>= 1;
-  GNO_CHECK_ARG(a % es == 0, "gno_segment_reduce: buffers not aligned to the element size");
 
   SegParams p;
-  p.rowptr = g->rowptr;
   p.gidx = g->gidx;
   p.eid = g->eid;
+  p.erow = g->erow;
   p.x = x;
   p.w = w;
   p.out = out;
   p.arg = arg;
-  p.hrow = g->hrow;
-  p.hcptr = g->hcptr;
+  p.rowptr = g->rowptr;
+  p.srow = g->srow;
+  p.zrow = g->zrow;
   p.N = g->N;
-  p.n_heavy = g->split_len > 0 ? g->n_heavy : 0;
-  p.n_chunks = g->split_len > 0 ? g->n_chunks : 0;
-  p.split_len = g->split_len;
+  p.E = g->E;
+  p.chunk_len = (int)g->chunk_len;
+  p.n_chunks = ceil_div(g->E, g->chunk_len);
+  p.n_span = g->n_span;
+  p.n_empty = g->n_empty;
   p.F = F;
   p.ldx_bytes = ldx * es;
   p.ldo_bytes = ldo * es;
@@ -492,18 +520,17 @@ int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows, int64_t 
   if (p.n_chunks > 0) {
     if (wsp == nullptr) return fail(GNO_ERR_WORKSPACE, "gno_segment_reduce: workspace is NULL");
     Workspace ws(wsp, ws_bytes);
-    p.part_val = ws.take<float>((size_t)(p.n_chunks * F));
+    p.part_val = ws.take<float>((size_t)(2 * p.n_chunks * F));
     if (reduce == GNO_MIN || reduce == GNO_MAX)
-      p.part_arg = ws.take<int32_t>((size_t)(p.n_chunks * F));
+      p.part_arg = ws.take<int32_t>((size_t)(2 * p.n_chunks * F));
     if (!ws.ok())
       return fail(GNO_ERR_WORKSPACE, "gno_segment_reduce: workspace too small (%zu < %zu)", ws_bytes, ws.off);
   }
-  const int64_t warps = (p.N + p.n_chunks) * p.ncoltiles;
   const bool has_w = (w != nullptr);
   switch (dtype) {
-    case GNO_F32: return dispatch_vb<float>(p, vb, reduce, with_arg, has_w, warps, s);
-    case GNO_F16: return dispatch_vb<__half>(p, vb, reduce, with_arg, has_w, warps, s);
-    case GNO_BF16: return dispatch_vb<__nv_bfloat16>(p, vb, reduce, with_arg, has_w, warps, s);
+    case GNO_F32: return dispatch_vb<float>(p, vb, reduce, with_arg, has_w, s);
+    case GNO_F16: return dispatch_vb<__half>(p, vb, reduce, with_arg, has_w, s);
+    case GNO_BF16: return dispatch_vb<__nv_bfloat16>(p, vb, reduce, with_arg, has_w, s);
   }
   return fail(GNO_ERR_INVALID, "gno_segment_reduce: unknown dtype %d", dtype);
 }

@@ -25,13 +25,14 @@ class gno_csr(Structure):
         ("N", c_int64),
         ("E", c_int64),
         ("rowptr", c_void_p),
+        ("erow", c_void_p),
         ("gidx", c_void_p),
         ("eid", c_void_p),
-        ("split_len", c_int64),
-        ("n_heavy", c_int64),
-        ("n_chunks", c_int64),
-        ("hrow", c_void_p),
-        ("hcptr", c_void_p),
+        ("chunk_len", c_int64),
+        ("n_span", c_int64),
+        ("srow", c_void_p),
+        ("n_empty", c_int64),
+        ("zrow", c_void_p),
     ]
 
 
@@ -46,13 +47,14 @@ PROTOTYPES = {
     "gno_sort_f32_workspace": (c_int, [c_int64, c_int64, c_int64, POINTER(c_size_t)]),
     "gno_sort_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int,
                              c_void_p, c_size_t, c_void_p]),
-    "gno_plan_heavy_capacity": (c_int64, [c_int64, c_int64]),
     "gno_plan_workspace": (c_int, [c_int64, c_int64, POINTER(c_size_t)]),
     "gno_plan_build": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
-                               c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "gno_plan_from_rowptr_workspace": (c_int, [c_int64, c_int64, POINTER(c_size_t)]),
+                               c_void_p, c_void_p, c_size_t, c_void_p]),
     "gno_plan_from_rowptr": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
-                                     c_void_p, c_void_p, c_size_t, c_void_p]),
+                                     c_void_p]),
+    "gno_plan_lists_workspace": (c_int, [c_int64, POINTER(c_size_t)]),
+    "gno_plan_lists": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                               c_void_p]),
     "gno_permute_i64_to_i32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "gno_narrow_i64_to_i32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "gno_permute_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),

@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from ._lib import (GNO_BF16, GNO_F16, GNO_F32, GNO_MAX, GNO_MEAN, GNO_MIN, GNO_MUL, GNO_SUM,
                    REDUCE_IDS, GnoError, check, lib)
-from .plan import (DEFAULT_SPLIT_LEN, CSRPlan, _ptr, _stream, _workspace, build_plan, plan_cache,
+from .plan import (CSRPlan, _ptr, _stream, _workspace, build_plan, plan_cache,
                    plan_from_rowptr)
 
 _DTYPES = {torch.float32: GNO_F32, torch.float16: GNO_F16, torch.bfloat16: GNO_BF16}

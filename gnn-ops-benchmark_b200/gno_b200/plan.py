@@ -1,8 +1,9 @@
 """Host side of the dst-sorted CSR plan (include/gno_b200.h: gno_plan_build).
 
 A plan is the reusable part of an aggregation: the stable argsort of the
-destination index (`perm`), the CSR `rowptr`, and the split table for rows
-longer than `split_len`.  GNN layers reuse one graph many times, so plans are
+destination index (`perm`), the CSR `rowptr`, the destination row of every
+sorted edge (`erow`), and the lists of rows the finish pass touches (rows cut
+by a chunk boundary, empty rows).  GNN layers reuse one graph many times, so plans are
 cached on the identity of the index tensor — the same role the rowptr /
 csr2csc caches play inside torch_sparse.SparseTensor upstream.
 """
@@ -14,7 +15,16 @@ import torch
 from . import _lib
 from ._lib import check, gno_csr, lib
 
-DEFAULT_SPLIT_LEN = 1024
+def default_chunk_len(num_edges):
+    """Edges per worker chunk: large enough that chunk-boundary partials are ~1 % of the
+    traffic, small enough that small inputs still fill 148 SMs."""
+    if num_edges >= (1 << 23):
+        return 256
+    if num_edges >= (1 << 21):
+        return 128
+    if num_edges >= (1 << 19):
+        return 64
+    return 32
 
 
 def _ptr(t):
@@ -30,10 +40,10 @@ def _workspace(nbytes, device):
 
 
 class CSRPlan:
-    """dst-sorted CSR of a 1-D index.  All arrays live on the index's device."""
+    """dst-sorted edge list of a 1-D index.  All arrays live on the index's device."""
 
-    __slots__ = ("N", "E", "rowptr", "perm", "split_len", "n_heavy", "n_chunks", "max_len",
-                 "n_dropped", "hrow", "hcptr", "device", "_gidx_cache", "_keepalive")
+    __slots__ = ("N", "E", "E_valid", "rowptr", "perm", "erow", "chunk_len", "n_span", "n_empty",
+                 "max_len", "n_dropped", "srow", "zrow", "device", "_gidx_cache", "_keepalive")
 
     def __init__(self):
         self._gidx_cache = collections.OrderedDict()
@@ -41,12 +51,13 @@ class CSRPlan:
 
     def csr(self, gidx, eid):
         """The C struct for one launch. gidx/eid: int32 tensors or None (identity)."""
-        return gno_csr(self.N, self.E, self.rowptr.data_ptr(),
+        return gno_csr(self.N, self.E_valid, self.rowptr.data_ptr(),
+                       self.erow.data_ptr() if self.erow is not None else None,
                        gidx.data_ptr() if gidx is not None else None,
                        eid.data_ptr() if eid is not None else None,
-                       self.split_len if self.n_heavy > 0 else 0, self.n_heavy, self.n_chunks,
-                       self.hrow.data_ptr() if self.n_heavy > 0 else None,
-                       self.hcptr.data_ptr() if self.n_heavy > 0 else None)
+                       self.chunk_len, self.n_span,
+                       self.srow.data_ptr() if self.n_span > 0 else None,
+                       self.n_empty, self.zrow.data_ptr() if self.n_empty > 0 else None)
 
     def sorted_ids(self, ids):
         """int32 copy of `ids` (int64 [E]) reordered by the plan: ids[perm]. Cached."""
@@ -62,9 +73,26 @@ class CSRPlan:
             self._gidx_cache.popitem(last=False)
         return out
 
+    def _finish(self, info):
+        """Read the device counters (one sync) and build the span / empty row lists."""
+        dev = self.device
+        self.n_dropped, self.max_len, self.n_span, self.n_empty = (int(v) for v in info.tolist())
+        self.E_valid = self.E - self.n_dropped
+        self.srow = torch.empty(self.n_span, dtype=torch.int32, device=dev)
+        self.zrow = torch.empty(self.n_empty, dtype=torch.int32, device=dev)
+        if self.n_span or self.n_empty:
+            nbytes = ctypes.c_size_t()
+            check(lib.gno_plan_lists_workspace(self.N, ctypes.byref(nbytes)))
+            ws = _workspace(nbytes.value, dev)
+            with torch.cuda.device(dev):
+                check(lib.gno_plan_lists(_ptr(self.rowptr), self.N, self.chunk_len,
+                                         _ptr(self.srow) if self.n_span else None,
+                                         _ptr(self.zrow) if self.n_empty else None,
+                                         _ptr(ws), ws.numel(), _stream(dev)))
 
-def build_plan(index, num_rows, split_len=DEFAULT_SPLIT_LEN):
-    """Sort `index` (1-D int64, CUDA) by destination and build rowptr + split table."""
+
+def build_plan(index, num_rows, chunk_len=None):
+    """Sort `index` (1-D int64, CUDA) by destination; build rowptr, per-edge rows, row lists."""
     if not index.is_cuda:
         raise _lib.GnoError("gno_b200 has no CPU path: index must be a CUDA tensor")
     if index.dim() != 1 or index.dtype != torch.int64:
@@ -73,27 +101,23 @@ def build_plan(index, num_rows, split_len=DEFAULT_SPLIT_LEN):
     dev = index.device
     E, N = index.numel(), int(num_rows)
     p = CSRPlan()
-    p.N, p.E, p.device, p.split_len = N, E, dev, int(split_len)
+    p.N, p.E, p.device = N, E, dev
+    p.chunk_len = int(chunk_len) if chunk_len else default_chunk_len(E)
     p.rowptr = torch.empty(N + 1, dtype=torch.int64, device=dev)
     p.perm = torch.empty(max(E, 1), dtype=torch.int32, device=dev)[:E]
-    cap = int(lib.gno_plan_heavy_capacity(E, p.split_len))
-    hrow = torch.empty(cap, dtype=torch.int32, device=dev)
-    hcptr = torch.empty(cap + 1, dtype=torch.int64, device=dev)
+    p.erow = torch.empty(max(E, 1), dtype=torch.int32, device=dev)[:E]
     info = torch.empty(4, dtype=torch.int64, device=dev)
     nbytes = ctypes.c_size_t()
     check(lib.gno_plan_workspace(E, N, ctypes.byref(nbytes)))
     ws = _workspace(nbytes.value, dev)
     with torch.cuda.device(dev):
-        check(lib.gno_plan_build(_ptr(index), E, N, p.split_len, _ptr(p.rowptr), _ptr(p.perm),
-                                 _ptr(info), _ptr(hrow), _ptr(hcptr), _ptr(ws), ws.numel(),
-                                 _stream(dev)))
-    p.n_dropped, p.max_len, p.n_heavy, p.n_chunks = (int(v) for v in info.tolist())  # one sync
-    p.hrow = hrow[:p.n_heavy]
-    p.hcptr = hcptr[:p.n_heavy + 1]
+        check(lib.gno_plan_build(_ptr(index), E, N, p.chunk_len, _ptr(p.rowptr), _ptr(p.perm),
+                                 _ptr(p.erow), _ptr(info), _ptr(ws), ws.numel(), _stream(dev)))
+    p._finish(info)
     return p
 
 
-def plan_from_rowptr(rowptr, nnz, split_len=DEFAULT_SPLIT_LEN):
+def plan_from_rowptr(rowptr, nnz, chunk_len=None):
     """Plan over a caller-supplied CSR rowptr (segment_csr / SparseTensor inputs)."""
     if not rowptr.is_cuda:
         raise _lib.GnoError("gno_b200 has no CPU path: rowptr must be a CUDA tensor")
@@ -101,21 +125,15 @@ def plan_from_rowptr(rowptr, nnz, split_len=DEFAULT_SPLIT_LEN):
     dev = rowptr.device
     N, E = rowptr.numel() - 1, int(nnz)
     p = CSRPlan()
-    p.N, p.E, p.device, p.split_len = N, E, dev, int(split_len)
+    p.N, p.E, p.device = N, E, dev
+    p.chunk_len = int(chunk_len) if chunk_len else default_chunk_len(E)
     p.rowptr, p.perm = rowptr, None
-    cap = int(lib.gno_plan_heavy_capacity(E, p.split_len))
-    hrow = torch.empty(cap, dtype=torch.int32, device=dev)
-    hcptr = torch.empty(cap + 1, dtype=torch.int64, device=dev)
+    p.erow = torch.empty(max(E, 1), dtype=torch.int32, device=dev)[:E]
     info = torch.empty(4, dtype=torch.int64, device=dev)
-    nbytes = ctypes.c_size_t()
-    check(lib.gno_plan_from_rowptr_workspace(N, E, ctypes.byref(nbytes)))
-    ws = _workspace(nbytes.value, dev)
     with torch.cuda.device(dev):
-        check(lib.gno_plan_from_rowptr(_ptr(rowptr), N, E, p.split_len, _ptr(info), _ptr(hrow),
-                                       _ptr(hcptr), _ptr(ws), ws.numel(), _stream(dev)))
-    p.n_dropped, p.max_len, p.n_heavy, p.n_chunks = (int(v) for v in info.tolist())
-    p.hrow = hrow[:p.n_heavy]
-    p.hcptr = hcptr[:p.n_heavy + 1]
+        check(lib.gno_plan_from_rowptr(_ptr(rowptr), N, E, p.chunk_len, _ptr(p.erow), _ptr(info),
+                                       _stream(dev)))
+    p._finish(info)
     return p
 
 
@@ -128,8 +146,8 @@ class PlanCache:
         self.hits = 0
         self.misses = 0
 
-    def get(self, index, num_rows, split_len=DEFAULT_SPLIT_LEN):
-        key = (index.data_ptr(), index._version, index.numel(), int(num_rows), int(split_len),
+    def get(self, index, num_rows, chunk_len=None):
+        key = (index.data_ptr(), index._version, index.numel(), int(num_rows), chunk_len,
                str(index.device))
         p = self._d.get(key)
         if p is not None:
@@ -137,7 +155,7 @@ class PlanCache:
             self.hits += 1
             return p
         self.misses += 1
-        p = build_plan(index, num_rows, split_len)
+        p = build_plan(index, num_rows, chunk_len)
         p._keepalive = index  # the key is a raw pointer: keep the tensor alive
         self._d[key] = p
         while len(self._d) > self.capacity:

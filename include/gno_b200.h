@@ -89,32 +89,38 @@ int gno_sort_f32(const float* in, float* out_values, int64_t* out_index,
 
 /* ---------------------------------------------------------------- plan -- */
 /*
- * Build the dst-sorted CSR plan of a 1-D int64 index vector (the
+ * Build the dst-sorted plan of a 1-D int64 index vector (the
  * "index"/edge_index[1] argument of torch_scatter.scatter,
  * op_bm_scripts/benchmark_scatter_add.py:18 in its message-passing form):
  *   perm   [E]   int32  stable argsort of index  (perm[k] = original edge id)
+ *   erow   [E]   int32  destination row of sorted edge k (the sorted keys;
+ *                        N for entries that were outside [0,N))
  *   rowptr [N+1] int64  rowptr[i] = first sorted position with index >= i
- *   info   [4]   int64  device scalars: [0] #entries outside [0,N) (those
- *                        are dropped from every row), [1] max row length,
- *                        [2] #rows longer than split_len, [3] #chunks those
- *                        rows split into
- *   hrow   [cap] int32  ids of rows longer than split_len (ascending)
- *   hcptr  [cap+1] int64 exclusive prefix of their chunk counts
- * cap = gno_plan_heavy_capacity(E, split_len).  Requires N < 2^31, E < 2^31.
+ *   info   [4]   int64  device scalars: [0] #entries outside [0,N) (they sort
+ *                        to the tail and belong to no row), [1] max row
+ *                        length, [2] #rows that span more than one
+ *                        chunk_len-edge chunk, [3] #empty rows
+ * The aggregation kernel gives every worker one chunk of `chunk_len`
+ * consecutive sorted edges (edge-balanced, so power-law rows cost nothing
+ * extra); rows cut by a chunk boundary are finished by a second pass.
+ * gno_plan_lists then materialises those rows (srow, ascending) and the
+ * empty rows (zrow) once the host has read info[2], info[3].
+ * Requires N < 2^31 - 1, E < 2^31, chunk_len a multiple of 32.
  */
-int64_t gno_plan_heavy_capacity(int64_t E, int64_t split_len);
 int gno_plan_workspace(int64_t E, int64_t N, size_t* bytes);
 int gno_plan_build(const int64_t* index, int64_t E, int64_t N,
-                   int64_t split_len, int64_t* rowptr, int32_t* perm,
-                   int64_t* info, int32_t* hrow, int64_t* hcptr, void* ws,
-                   size_t ws_bytes, gno_stream_t stream);
-/* Same heavy-row analysis for a caller-supplied CSR rowptr (torch_sparse
- * SparseTensor / segment_csr inputs): fills info[1..3], hrow, hcptr. */
-int gno_plan_from_rowptr_workspace(int64_t N, int64_t E, size_t* bytes);
+                   int64_t chunk_len, int64_t* rowptr, int32_t* perm,
+                   int32_t* erow, int64_t* info, void* ws, size_t ws_bytes,
+                   gno_stream_t stream);
+/* Same for a caller-supplied CSR rowptr (torch_sparse SparseTensor /
+ * segment_csr inputs): expands erow and fills info[1..3]. */
 int gno_plan_from_rowptr(const int64_t* rowptr, int64_t N, int64_t E,
-                         int64_t split_len,
-                         int64_t* info, int32_t* hrow, int64_t* hcptr,
-                         void* ws, size_t ws_bytes, gno_stream_t stream);
+                         int64_t chunk_len, int32_t* erow, int64_t* info,
+                         gno_stream_t stream);
+int gno_plan_lists_workspace(int64_t N, size_t* bytes);
+int gno_plan_lists(const int64_t* rowptr, int64_t N, int64_t chunk_len,
+                   int32_t* srow, int32_t* zrow, void* ws, size_t ws_bytes,
+                   gno_stream_t stream);
 
 /* out[k] = (int32) src[perm[k]]  — builds the sorted source-id array of the
  * fused gather→scatter form (edge_index[0] reordered by the plan). */
@@ -134,25 +140,27 @@ int gno_permute_rows(const void* src, const int32_t* perm, void* out,
  */
 typedef struct gno_csr {
   int64_t N;             /* destination rows */
-  int64_t E;             /* sorted edges */
+  int64_t E;             /* sorted edges that belong to a row (= rowptr[N]) */
   const int64_t* rowptr; /* [N+1] */
+  const int32_t* erow;   /* [E] destination row of sorted edge k */
   const int32_t* gidx;   /* [E] row of x to gather for sorted edge k;
                             NULL = k itself (segment_csr form) */
   const int32_t* eid;    /* [E] value reported by arg outputs for edge k
                             (original edge position); NULL = k */
-  int64_t split_len;     /* rows longer than this are split; 0 = never */
-  int64_t n_heavy;       /* info[2] */
-  int64_t n_chunks;      /* info[3] */
-  const int32_t* hrow;   /* [n_heavy] */
-  const int64_t* hcptr;  /* [n_heavy+1] */
+  int64_t chunk_len;     /* edges per worker chunk the lists were built for */
+  int64_t n_span;        /* info[2] */
+  const int32_t* srow;   /* [n_span] rows cut by a chunk boundary */
+  int64_t n_empty;       /* info[3] */
+  const int32_t* zrow;   /* [n_empty] rows without edges */
 } gno_csr;
 
 /*
  * out[i, :] = reduce over sorted edges k in row i of  w[k] * x[gidx[k], :]
  * — the one kernel family behind scatter sum/mean/mul/min/max (+arg), the
  * fused index_select→scatter_add / index_add_ gather-reduce, segment_csr and
- * CSR spmm.  Warp-per-destination-row, atomic-free and deterministic; fp32
- * accumulation for every dtype, one rounding at the end.
+ * CSR spmm.  Edge-balanced segmented reduction (one chunk of sorted edges per
+ * lane group), atomic-free and deterministic; fp32 accumulation for every
+ * dtype, one rounding at the end.
  *
  *   x        [x_rows, F] with row stride ldx elements
  *   w        [E] per-sorted-edge weights in x's dtype, or NULL (spmm value)
@@ -162,7 +170,7 @@ typedef struct gno_csr {
  *            arg_fill and out 0 (torch_scatter semantics)
  *   accumulate  non-zero: combine with the values already in out
  *            (index_add_ / out= forms; SUM and MUL only)
- *   ws       >= gno_segment_reduce_workspace(...) bytes (split-row partials)
+ *   ws       >= gno_segment_reduce_workspace(...) bytes (chunk-boundary partials)
  *
  * Replaces: scatter_add/mean/max/min (op_bm_scripts/benchmark_scatter_add.py:18,
  * _mean.py:17, _max.py:17, _min.py:17), scatter_(reduce="multiply")

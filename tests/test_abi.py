@@ -38,7 +38,7 @@ def test_abi_argument_validation_without_gpu():
     assert b"key_bytes" in lib.gno_last_error()
     assert lib.gno_plan_workspace(1 << 31, 10, ctypes.byref(n)) == 1
     assert lib.gno_plan_workspace(10, 10, ctypes.byref(n)) == 0
-    assert lib.gno_plan_heavy_capacity(1000, 100) == 11
+    assert lib.gno_plan_lists_workspace(1000, ctypes.byref(n)) == 0 and n.value >= 16000
     with pytest.raises(_lib.GnoError):
         _lib.check(lib.gno_coalesce_workspace(-1, 1, 1, 1, 0, ctypes.byref(n)))
     assert lib.gno_launch_count() >= 0

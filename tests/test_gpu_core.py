@@ -56,26 +56,30 @@ def test_plan_build(cuda, E, N):
     import gno_b200
     g = torch.Generator().manual_seed(E + N)
     idx = torch.randint(0, N, (E,), generator=g)
-    plan = gno_b200.build_plan(idx.to(cuda), N, split_len=64)
+    C = 64
+    plan = gno_b200.build_plan(idx.to(cuda), N, chunk_len=C)
     rowptr, perm = oracle.csr_from_index(idx, N)
     assert torch.equal(plan.rowptr.cpu(), rowptr)
     assert torch.equal(plan.perm.cpu().to(torch.int64), perm)
+    assert torch.equal(plan.erow.cpu().to(torch.int64), idx[perm])
     deg = rowptr[1:] - rowptr[:-1]
     assert plan.max_len == (int(deg.max()) if N else 0)
-    heavy = torch.nonzero(deg > 64).flatten()
-    assert plan.n_heavy == heavy.numel()
-    assert torch.equal(plan.hrow.cpu().to(torch.int64), heavy)
-    chunks = (deg[heavy] + 63) // 64
-    assert plan.n_chunks == int(chunks.sum())
-    assert plan.n_dropped == 0
+    empty = torch.nonzero(deg == 0).flatten()
+    span = torch.nonzero((deg > 0) & (rowptr[:-1] // C != (rowptr[1:] - 1) // C)).flatten()
+    assert plan.n_empty == empty.numel() and torch.equal(plan.zrow.cpu().to(torch.int64), empty)
+    assert plan.n_span == span.numel() and torch.equal(plan.srow.cpu().to(torch.int64), span)
+    assert plan.n_dropped == 0 and plan.E_valid == E
 
 
 def test_plan_out_of_range(cuda):
     import gno_b200
     idx = torch.tensor([3, -1, 0, 7, 2, 3, 100], dtype=torch.int64)
     plan = gno_b200.build_plan(idx.to(cuda), 5)
-    assert plan.n_dropped == 3
+    assert plan.n_dropped == 3 and plan.E_valid == 4
     assert plan.rowptr.cpu().tolist() == [0, 1, 1, 2, 4, 4]
+    src = torch.arange(7, dtype=torch.float32).view(7, 1) + 1
+    out = gno_b200.scatter(src.to(cuda), idx.to(cuda), 0, None, 5, "sum")
+    assert out.cpu().view(-1).tolist() == [3.0, 0.0, 5.0, 7.0, 0.0]  # out-of-range entries are dropped
 
 
 CASES = [  # E, N, F
@@ -117,9 +121,10 @@ def test_scatter_1d_index(cuda, dtype, reduce, E, N, F):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("reduce", ["sum", "mean", "min", "max"])
 @pytest.mark.parametrize("E,N,F,split", [(30000, 20, 100, 64), (30000, 20, 602, 128), (20000, 300, 64, 32),
-                                         (50000, 3, 16, 1024)])
+                                         (50000, 3, 16, 1024), (30000, 5000, 100, 256), (70001, 40, 8, 32)])
 def test_gather_scatter_split_rows(cuda, dtype, reduce, E, N, F, split):
-    """Fused gather→scatter with heavy rows split into chunks (power-law path)."""
+    """Fused gather→scatter on skewed graphs for several chunk lengths: rows far longer than a
+    chunk (many partials combined in order) and many rows per chunk (power-law path)."""
     import gno_b200
     from gno_b200 import plan as planmod
     gno_b200.clear_caches()
@@ -133,16 +138,11 @@ def test_gather_scatter_split_rows(cuda, dtype, reduce, E, N, F, split):
     dst = (torch.rand(E, generator=g) ** 4 * N).long().clamp_(0, N - 1)
     src_ids = torch.randint(0, n_src, (E,), generator=g)
     want, want_arg = oracle.gather_scatter(x, src_ids, dst, N, reduce)
-    old = planmod.DEFAULT_SPLIT_LEN
-    try:
-        dst_c = dst.to(cuda)
-        plan = planmod.build_plan(dst_c, N, split_len=split)
-        assert plan.n_heavy > 0
-        gidx = plan.sorted_ids(src_ids.to(cuda))
-        r = gno_b200.segment_reduce(plan, x.to(cuda), reduce, gidx=gidx, eid=plan.perm,
-                                    want_arg=reduce in ("min", "max"), arg_fill=E)
-    finally:
-        planmod.DEFAULT_SPLIT_LEN = old
+    plan = planmod.build_plan(dst.to(cuda), N, chunk_len=split)
+    assert plan.n_span > 0
+    gidx = plan.sorted_ids(src_ids.to(cuda))
+    r = gno_b200.segment_reduce(plan, x.to(cuda), reduce, gidx=gidx, eid=plan.perm,
+                                want_arg=reduce in ("min", "max"), arg_fill=E)
     if reduce in ("min", "max"):
         assert torch.equal(r[0].cpu(), want)
         assert torch.equal(r[1].cpu(), want_arg)
