@@ -27,6 +27,13 @@ namespace gno {
 
 constexpr int kSegThreads = 128;
 constexpr int kSegWarps = kSegThreads / 32;
+#ifndef GNO_SEG_MINB
+#define GNO_SEG_MINB 8  // cap registers at 64: 32 resident warps per SM
+#endif
+#ifndef GNO_SEG_INFLIGHT
+#define GNO_SEG_INFLIGHT 64  // bytes of gathered rows in flight per lane (sets the unroll U)
+#endif
+constexpr int kSegMinBlocks = GNO_SEG_MINB;
 constexpr int kNoArg = INT_MAX;
 
 struct SegParams {
@@ -206,27 +213,54 @@ __device__ __forceinline__ void flush_row(const SegParams& p, int64_t row, int64
   st_vec<VB>(optr, o);
 }
 
+// acc (+= | *= | min | max)= one gathered vector
+template <typename T, int VB, int RED, bool ARG, bool HAS_W>
+__device__ __forceinline__ void accumulate(float (&acc)[VB / (int)sizeof(T)],
+                                           int (&ae)[ARG ? VB / (int)sizeof(T) : 1],
+                                           const Words<VB>& val, int e, float w) {
+  constexpr int EPV = VB / (int)sizeof(T);
+#pragma unroll
+  for (int i = 0; i < EPV; ++i) {
+    const float f = elem<T, VB>(val, i);
+    if constexpr (RED == GNO_SUM) {
+      if constexpr (HAS_W) acc[i] = fmaf(w, f, acc[i]);
+      else acc[i] += f;
+    } else if constexpr (RED == GNO_MUL) {
+      acc[i] *= f;
+    } else {
+      if (better<RED>(f, acc[i])) {
+        acc[i] = f;
+        if constexpr (ARG) ae[i] = e;
+      }
+    }
+  }
+}
+
 template <typename T, int VB, int RED, bool ARG, bool HAS_W, int U>
-__global__ void __launch_bounds__(kSegThreads) segreduce_kernel(const SegParams p) {
+__global__ void __launch_bounds__(kSegThreads, kSegMinBlocks) segreduce_kernel(const SegParams p) {
   constexpr int EPV = VB / (int)sizeof(T);
   const int lane = threadIdx.x & 31;
   const int G = p.G;
-  const int grp = lane / G;       // worker within the warp
   const int li = lane & (G - 1);  // lane within the worker
   const int gbase = lane - li;
   const int64_t warp = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5);
-  const int64_t wk = warp * (32 / G) + grp;
+  const int64_t wk = warp * (32 / G) + lane / G;
   const int64_t chunk = wk / p.ncoltiles;
   const int ct = (int)(wk - chunk * p.ncoltiles);
   const int C = p.chunk_len;
   const bool active = chunk < p.n_chunks;
   const int64_t k0 = chunk * C;
-  const int64_t k1 = active ? imin64(k0 + C, p.E) : k0;
+  const int nv = active ? (int)imin64(C, p.E - k0) : 0;  // edges in this chunk
   const int v = ct * 32 + li;
   const bool vact = active && (v < p.nvec);
   const char* xcol = static_cast<const char*>(p.x) + (int64_t)v * VB;
+  const unsigned ldx = (unsigned)p.ldx_bytes;
   const bool stream_idx = (p.ncoltiles == 1);
   const uint64_t pol_stream = l2_policy_evict_first();
+  const int32_t* erow = p.erow + k0;
+  const int32_t* gidx = p.gidx ? p.gidx + k0 : nullptr;
+  const int32_t* eid = p.eid ? p.eid + k0 : nullptr;
+  const T* wgt = HAS_W ? static_cast<const T*>(p.w) + k0 : nullptr;
 
   float acc[EPV];
   int ae[ARG ? EPV : 1];
@@ -236,88 +270,95 @@ __global__ void __launch_bounds__(kSegThreads) segreduce_kernel(const SegParams 
 #pragma unroll
     for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
   }
-  int cur_row = active ? __ldg(p.erow + k0) : 0;
-  bool head = active && k0 > 0 && __ldg(p.erow + k0 - 1) == cur_row;
-  int64_t seg_start = k0;
+  int cur_row = active ? __ldg(erow) : 0;
+  bool head = active && k0 > 0 && __ldg(erow - 1) == cur_row;
+  int seg_start = 0;  // chunk-relative position where cur_row's segment began
 
-  for (int t = 0; t < C; t += G) {
-    // stage G edge records in the worker's lanes (coalesced)
-    const int64_t k = k0 + t + li;
-    int my_idx = 0, my_row = 0, my_e = 0;
-    float my_w = 0.f;
-    if (k < k1) {
-      my_row = stream_idx ? ld_stream_i32(p.erow + k, pol_stream) : __ldg(p.erow + k);
-      if (p.gidx)
-        my_idx = stream_idx ? ld_stream_i32(p.gidx + k, pol_stream) : __ldg(p.gidx + k);
-      else
-        my_idx = (int)k;
+  // One staged tile = G edge records, one per lane of the worker.
+  auto stage = [&](int t, int& s_idx, int& s_row, int& s_e, float& s_w) {
+    const int k = t + li;
+    s_idx = 0; s_row = 0; s_e = 0; s_w = 0.f;
+    if (k < nv) {
+      s_row = stream_idx ? ld_stream_i32(erow + k, pol_stream) : __ldg(erow + k);
+      if (gidx) s_idx = stream_idx ? ld_stream_i32(gidx + k, pol_stream) : __ldg(gidx + k);
+      else s_idx = (int)(k0 + k);
       if constexpr (ARG) {
-        if (p.eid == p.gidx)
-          my_e = my_idx;
-        else if (p.eid)
-          my_e = stream_idx ? ld_stream_i32(p.eid + k, pol_stream) : __ldg(p.eid + k);
-        else
-          my_e = (int)k;
+        if (p.eid == p.gidx) s_e = s_idx;
+        else if (eid) s_e = stream_idx ? ld_stream_i32(eid + k, pol_stream) : __ldg(eid + k);
+        else s_e = (int)(k0 + k);
       }
-      if constexpr (HAS_W) my_w = DType<T>::to_f(static_cast<const T*>(p.w)[k]);
+      if constexpr (HAS_W) s_w = DType<T>::to_f(wgt[k]);
     }
+  };
+
+  int my_idx, my_row, my_e;
+  float my_w;
+  stage(0, my_idx, my_row, my_e, my_w);
+  for (int t = 0; t < C; t += G) {
+    // prefetch the next tile's records while this tile's rows are gathered
+    int nx_idx = 0, nx_row = 0, nx_e = 0;
+    float nx_w = 0.f;
+    if (t + G < C) stage(t + G, nx_idx, nx_row, nx_e, nx_w);
+    const int rem = nv - t;  // valid edges from this tile on (may be <= 0)
     for (int j = 0; j < G; j += U) {
       Words<VB> val[U];
-      int row_u[U];
       int e_u[ARG ? U : 1];
       float w_u[HAS_W ? U : 1];
-      bool ok[U];
+      // a batch is "plain" when every slot is a real edge (U <= G and no chunk tail)
+      const bool plain = (j + U <= G) && (j + U <= rem);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int slot = j + u;
         const int src_lane = gbase + (slot & (G - 1));
         const int idx = __shfl_sync(0xffffffffu, my_idx, src_lane);
-        row_u[u] = __shfl_sync(0xffffffffu, my_row, src_lane);
         if constexpr (ARG) e_u[u] = __shfl_sync(0xffffffffu, my_e, src_lane);
         if constexpr (HAS_W) w_u[u] = __shfl_sync(0xffffffffu, my_w, src_lane);
-        ok[u] = (slot < G) && (k0 + t + slot < k1);
-        if (ok[u] && vact) val[u] = ld_vec<VB>(xcol + (int64_t)idx * p.ldx_bytes);
+        if (vact && (plain || (slot < G && slot < rem)))
+          val[u] = ld_vec<VB>(xcol + (uint64_t)((unsigned)idx) * ldx);
       }
+      // row of the batch's last edge: rows ascend, so equal to cur_row means no boundary inside
+      const int last_slot = gbase + ((j + U - 1) & (G - 1));
+      const int row_last = __shfl_sync(0xffffffffu, my_row, last_slot);
+      const bool simple = plain && (row_last == cur_row);
+      if (__all_sync(0xffffffffu, simple || !active)) {
+        if (vact) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (ok[u]) {
-          if (row_u[u] != cur_row) {  // the previous row ended inside this chunk
-            const int64_t kk = k0 + t + j + u;
-            if (vact) flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, false, kk - seg_start, v, acc, ae);
-            head = false;
-            cur_row = row_u[u];
-            seg_start = kk;
+          for (int u = 0; u < U; ++u)
+            accumulate<T, VB, RED, ARG, HAS_W>(acc, ae, val[u], ARG ? e_u[ARG ? u : 0] : 0,
+                                               HAS_W ? w_u[HAS_W ? u : 0] : 0.f);
+        }
+      } else {
 #pragma unroll
-            for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
-            if constexpr (ARG) {
+        for (int u = 0; u < U; ++u) {
+          const int slot = j + u;
+          const int row_u = __shfl_sync(0xffffffffu, my_row, gbase + (slot & (G - 1)));
+          if (slot < G && slot < rem) {
+            if (row_u != cur_row) {  // the previous row ended inside this chunk
+              const int kk = t + slot;
+              if (vact)
+                flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, false, kk - seg_start, v, acc, ae);
+              head = false;
+              cur_row = row_u;
+              seg_start = kk;
 #pragma unroll
-              for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
-            }
-          }
-          if (vact) {
+              for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
+              if constexpr (ARG) {
 #pragma unroll
-            for (int i = 0; i < EPV; ++i) {
-              const float f = elem<T, VB>(val[u], i);
-              if constexpr (RED == GNO_SUM) {
-                if constexpr (HAS_W) acc[i] = fmaf(w_u[u], f, acc[i]);
-                else acc[i] += f;
-              } else if constexpr (RED == GNO_MUL) {
-                acc[i] *= f;
-              } else {
-                if (better<RED>(f, acc[i])) {
-                  acc[i] = f;
-                  if constexpr (ARG) ae[i] = e_u[u];
-                }
+                for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
               }
             }
+            if (vact)
+              accumulate<T, VB, RED, ARG, HAS_W>(acc, ae, val[u], ARG ? e_u[ARG ? u : 0] : 0,
+                                                 HAS_W ? w_u[HAS_W ? u : 0] : 0.f);
           }
         }
       }
     }
+    my_idx = nx_idx; my_row = nx_row; my_e = nx_e; my_w = nx_w;
   }
-  if (vact && k1 > k0) {
-    const bool tail = (k1 < p.E) && (__ldg(p.erow + k1) == cur_row);
-    flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, tail, k1 - seg_start, v, acc, ae);
+  if (vact && nv > 0) {
+    const bool tail = (k0 + nv < p.E) && (__ldg(erow + nv) == cur_row);
+    flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, tail, nv - seg_start, v, acc, ae);
   }
 }
 
@@ -376,7 +417,7 @@ __global__ void __launch_bounds__(256) segfinish_kernel(const SegParams p) {
 // ------------------------------------------------------------- dispatch --
 template <typename T, int VB, int RED, bool ARG, bool HAS_W>
 static int launch_seg(const SegParams& p, cudaStream_t s) {
-  constexpr int U = VB >= 16 ? 8 : 16;
+  constexpr int U = (GNO_SEG_INFLIGHT / VB) > 16 ? 16 : (GNO_SEG_INFLIGHT / VB);
   const int64_t workers = p.n_chunks * p.ncoltiles;
   const int64_t warps = ceil_div(workers, 32 / p.G);
   const int64_t blocks = ceil_div(warps, kSegWarps);
