@@ -199,16 +199,24 @@ def run_ours(args):
     x_full = torch.empty(n_global, F, device=dev, dtype=dtype) if world > 1 else x_local
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    plan = planmod.build_plan(dst, n_local)
-    gidx = plan.sorted_ids(src)
+    agg = None
+    if world > 1:
+        from gno_b200.dist import DistAggregator
+        bounds = torch.arange(world + 1, dtype=torch.int64) * n_local
+        agg = DistAggregator(bounds, src, dst, rank=rank, world=world)
+        plan, gidx = agg.plan()
+    else:
+        plan = planmod.build_plan(dst, n_local)
+        gidx = plan.sorted_ids(src)
     torch.cuda.synchronize()
     plan_ms = (time.perf_counter() - t0) * 1e3
     out = torch.empty(n_local, F, device=dev, dtype=dtype)
 
     def step():
-        if world > 1:
-            dist.all_gather_into_tensor(x_full, x_local)
-        gno_b200.segment_reduce(plan, x_full, "sum", gidx=gidx, out=out)
+        if world > 1:  # NCCL all-gather of the feature shards, then the local gather-reduce
+            agg.aggregate(x_local, "sum", x_full=x_full, out=out)
+        else:
+            gno_b200.segment_reduce(plan, x_full, "sum", gidx=gidx, out=out)
 
     def barrier():
         if world > 1:
@@ -269,11 +277,10 @@ def run_ours(args):
             xd = x_host.to(dev, non_blocking=True)
             eid = ei_host.to(dev, non_blocking=True)
             if world > 1:
-                dist.all_gather_into_tensor(x_full, xd)
-                xs = x_full
+                a2 = DistAggregator(bounds, eid[0], eid[1], rank=rank, world=world)
+                o = a2.aggregate(xd, "sum", x_full=x_full)
             else:
-                xs = xd
-            o = gno_b200.gather_scatter(xs, eid[0], eid[1], n_local, "sum")
+                o = gno_b200.gather_scatter(xd, eid[0], eid[1], n_local, "sum")
             out_host.copy_(o, non_blocking=True)
 
         e2e_step()

@@ -139,6 +139,18 @@ int gno_gather_rows(const void* x, int64_t x_rows, int64_t row_bytes, const int6
   return GNO_OK;
 }
 
+int gno_pad_rows(const void* src, int64_t rows, int64_t row_bytes, int64_t src_stride_bytes,
+                 void* dst, int64_t dst_stride_bytes, gno_stream_t stream) {
+  if (rows == 0 || row_bytes == 0) return GNO_OK;
+  GNO_CHECK_ARG(src && dst && rows > 0 && row_bytes > 0 && src_stride_bytes >= row_bytes &&
+                    dst_stride_bytes >= row_bytes,
+                "gno_pad_rows: bad argument");
+  GNO_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_stride_bytes, src, (size_t)src_stride_bytes,
+                             (size_t)row_bytes, (size_t)rows, cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+  return GNO_OK;
+}
+
 int gno_segment_reduce_lastdim(const gno_csr* g, const void* x, int64_t B, int64_t L, int64_t ldx,
                                void* out, int64_t ldo, int64_t* arg, int64_t arg_fill, int dtype,
                                int reduce, int accumulate, gno_stream_t stream) {

@@ -51,6 +51,7 @@ struct SegParams {
   const int32_t* zrow;
   int64_t N, E, n_chunks, n_span, n_empty;
   int64_t F;
+  int64_t Fp;  // row stride of the partial buffers: F rounded up to 8 elements
   int64_t ldx_bytes, ldo_bytes;
   int64_t arg_fill;
   int chunk_len;  // edges per worker
@@ -59,6 +60,7 @@ struct SegParams {
   int G;          // lanes per worker (power of two; 32 when ncoltiles > 1)
   int mean;       // divide by max(row length, 1)
   int accumulate;
+  int vec_out;    // out rows are aligned for VB-byte vector stores and F*s is a multiple of VB
 };
 
 template <int VB>
@@ -184,33 +186,53 @@ __device__ __forceinline__ void flush_row(const SegParams& p, int64_t row, int64
   if (head || tail) {
     // a chunk that lies entirely inside one row is both: it uses the head slot
     const int64_t slot = 2 * chunk + (head ? 0 : 1);
-    float* pv = p.part_val + slot * p.F + (int64_t)v * EPV;
+    float* pv = p.part_val + slot * p.Fp + (int64_t)v * EPV;
 #pragma unroll
     for (int i = 0; i < EPV; ++i) pv[i] = acc[i];
     if constexpr (ARG) {
-      int32_t* pa = p.part_arg + slot * p.F + (int64_t)v * EPV;
+      int32_t* pa = p.part_arg + slot * p.Fp + (int64_t)v * EPV;
 #pragma unroll
       for (int i = 0; i < EPV; ++i) pa[i] = ae[i];
     }
     return;
   }
-  char* optr = static_cast<char*>(p.out) + row * p.ldo_bytes + (int64_t)v * VB;
-  Words<VB> prev;
-  if (p.accumulate) prev = ld_vec<VB>(optr);
   const float cnt = p.mean ? (float)imax64(seg_len, 1) : 0.f;
-  Words<VB> o;
+  if (p.vec_out) {
+    char* optr = static_cast<char*>(p.out) + row * p.ldo_bytes + (int64_t)v * VB;
+    Words<VB> prev;
+    if (p.accumulate) prev = ld_vec<VB>(optr);
+    Words<VB> o;
 #pragma unroll
-  for (int i = 0; i < EPV; ++i) {
-    int64_t* ap = nullptr;
-    int e = kNoArg;
-    if constexpr (ARG) {
-      if (p.arg) ap = p.arg + row * p.F + (int64_t)v * EPV + i;
-      e = ae[i];
+    for (int i = 0; i < EPV; ++i) {
+      int64_t* ap = nullptr;
+      int e = kNoArg;
+      if constexpr (ARG) {
+        if (p.arg) ap = p.arg + row * p.F + (int64_t)v * EPV + i;
+        e = ae[i];
+      }
+      const float pf = p.accumulate ? elem<T, VB>(prev, i) : 0.f;
+      set_elem<T, VB>(o, i, finalize<T, RED>(acc[i], e, pf, cnt, p.accumulate, p.arg_fill, ap));
     }
-    const float pf = p.accumulate ? elem<T, VB>(prev, i) : 0.f;
-    set_elem<T, VB>(o, i, finalize<T, RED>(acc[i], e, pf, cnt, p.accumulate, p.arg_fill, ap));
+    st_vec<VB>(optr, o);
+  } else {
+    // rows gathered with vectors wider than the output alignment (padded x): element stores,
+    // dropping the padding columns.  Rare relative to the gathers.
+    T* orow = reinterpret_cast<T*>(static_cast<char*>(p.out) + row * p.ldo_bytes);
+#pragma unroll
+    for (int i = 0; i < EPV; ++i) {
+      const int64_t col = (int64_t)v * EPV + i;
+      if (col < p.F) {
+        int64_t* ap = nullptr;
+        int e = kNoArg;
+        if constexpr (ARG) {
+          if (p.arg) ap = p.arg + row * p.F + col;
+          e = ae[i];
+        }
+        const float pf = p.accumulate ? DType<T>::to_f(orow[col]) : 0.f;
+        orow[col] = DType<T>::from_f(finalize<T, RED>(acc[i], e, pf, cnt, p.accumulate, p.arg_fill, ap));
+      }
+    }
   }
-  st_vec<VB>(optr, o);
 }
 
 // acc (+= | *= | min | max)= one gathered vector
@@ -365,50 +387,104 @@ __global__ void __launch_bounds__(kSegThreads, kSegMinBlocks) segreduce_kernel(c
 // Finish pass: (a) rows cut by a chunk boundary — combine their partials in
 // chunk order: the tail slot of the first chunk, then the head slot of every
 // later chunk; (b) empty rows — write zeros (and arg_fill).  One thread per
-// (row, feature).
+// (row, 4 consecutive features).
 template <typename T, int RED, bool ARG>
 __global__ void __launch_bounds__(256) segfinish_kernel(const SegParams p) {
-  const int64_t n_a = p.n_span * p.F;
-  const int64_t total = n_a + (p.accumulate ? 0 : p.n_empty * p.F);
+  const int64_t Q = (p.F + 3) / 4;  // feature quads per row
+  const int64_t n_a = p.n_span * Q;
+  const int64_t total = n_a + (p.accumulate ? 0 : p.n_empty * Q);
+  const bool vec_val = ((uintptr_t)p.out % (4 * sizeof(T)) == 0) && (p.ldo_bytes % (4 * sizeof(T)) == 0);
+  const bool vec_arg = ARG && p.arg && ((uintptr_t)p.arg % 16 == 0) && (p.F % 2 == 0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
+    float a[4];
+    int e[4];
+    int64_t row, f0;
+    float cnt = 0.f;
     if (i < n_a) {
-      const int64_t s = i / p.F, f = i - s * p.F;
-      const int64_t row = p.srow[s];
+      const int64_t s = i / Q;
+      f0 = (i - s * Q) * 4;
+      row = p.srow[s];
       const int64_t kb = p.rowptr[row], ke = p.rowptr[row + 1];
       const int64_t ca = kb / p.chunk_len, cb = (ke - 1) / p.chunk_len;
-      float a = p.part_val[(2 * ca + 1) * p.F + f];
-      int e = kNoArg;
-      if constexpr (ARG) e = p.part_arg[(2 * ca + 1) * p.F + f];
+      const float4 t = *reinterpret_cast<const float4*>(p.part_val + (2 * ca + 1) * p.Fp + f0);
+      a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
+      if constexpr (ARG) {
+        const int4 u = *reinterpret_cast<const int4*>(p.part_arg + (2 * ca + 1) * p.Fp + f0);
+        e[0] = u.x; e[1] = u.y; e[2] = u.z; e[3] = u.w;
+      } else {
+        e[0] = e[1] = e[2] = e[3] = kNoArg;
+      }
       for (int64_t c = ca + 1; c <= cb; ++c) {
-        const float pv = p.part_val[(2 * c) * p.F + f];
-        if constexpr (RED == GNO_SUM) {
-          a += pv;
-        } else if constexpr (RED == GNO_MUL) {
-          a *= pv;
-        } else {
-          // chunks ascend in edge position, so a strict compare keeps the lowest
-          if (better<RED>(pv, a)) {
-            a = pv;
-            if constexpr (ARG) e = p.part_arg[(2 * c) * p.F + f];
+        const float4 t2 = *reinterpret_cast<const float4*>(p.part_val + (2 * c) * p.Fp + f0);
+        const float pv[4] = {t2.x, t2.y, t2.z, t2.w};
+        int pe[4] = {0, 0, 0, 0};
+        if constexpr (ARG) {
+          const int4 u2 = *reinterpret_cast<const int4*>(p.part_arg + (2 * c) * p.Fp + f0);
+          pe[0] = u2.x; pe[1] = u2.y; pe[2] = u2.z; pe[3] = u2.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (RED == GNO_SUM) {
+            a[j] += pv[j];
+          } else if constexpr (RED == GNO_MUL) {
+            a[j] *= pv[j];
+          } else {
+            // chunks ascend in edge position, so a strict compare keeps the lowest
+            if (better<RED>(pv[j], a[j])) {
+              a[j] = pv[j];
+              e[j] = pe[j];
+            }
           }
         }
       }
-      T* op = reinterpret_cast<T*>(static_cast<char*>(p.out) + row * p.ldo_bytes) + f;
-      const float prev = p.accumulate ? DType<T>::to_f(*op) : 0.f;
-      const float cnt = p.mean ? (float)imax64(ke - kb, 1) : 0.f;
-      const float r = finalize<T, RED>(a, e, prev, cnt, p.accumulate, p.arg_fill,
-                                       (ARG && p.arg) ? p.arg + row * p.F + f : nullptr);
-      *op = DType<T>::from_f(r);
+      if (p.mean) cnt = (float)imax64(ke - kb, 1);
     } else {
       const int64_t j = i - n_a;
-      const int64_t z = j / p.F, f = j - z * p.F;
-      const int64_t row = p.zrow[z];
-      T* op = reinterpret_cast<T*>(static_cast<char*>(p.out) + row * p.ldo_bytes) + f;
-      // torch_scatter: empty rows are 0 for sum/mean/min/max and 1 for mul
-      *op = DType<T>::from_f(RED == GNO_MUL ? 1.f : 0.f);
-      if constexpr (ARG) {
-        if (p.arg) p.arg[row * p.F + f] = p.arg_fill;
+      const int64_t z = j / Q;
+      f0 = (j - z * Q) * 4;
+      row = p.zrow[z];
+      // no edge: the reduction's identity, which finalize turns into torch_scatter's
+      // empty-row value (0 for sum/mean/min/max with arg_fill, 1 for mul)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a[q] = red_init<T, RED>();
+        e[q] = kNoArg;
+      }
+    }
+    T* orow = reinterpret_cast<T*>(static_cast<char*>(p.out) + row * p.ldo_bytes);
+    int64_t* arow = (ARG && p.arg) ? p.arg + row * p.F : nullptr;
+    const bool full = (f0 + 4 <= p.F);
+    float r[4];
+    int64_t ra[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool in = (f0 + q < p.F);
+      const float prev = (p.accumulate && in) ? DType<T>::to_f(orow[f0 + q]) : 0.f;
+      int64_t av = 0;
+      r[q] = finalize<T, RED>(a[q], e[q], prev, cnt, p.accumulate, p.arg_fill, arow ? &av : nullptr);
+      ra[q] = av;
+    }
+    if (full && vec_val) {
+      Words<4 * sizeof(T)> o;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) set_elem<T, 4 * sizeof(T)>(o, q, r[q]);
+      st_vec<4 * sizeof(T)>(reinterpret_cast<char*>(orow + f0), o);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (f0 + q < p.F) orow[f0 + q] = DType<T>::from_f(r[q]);
+    }
+    if constexpr (ARG) {
+      if (arow) {
+        if (full && vec_arg) {
+          *reinterpret_cast<longlong2*>(arow + f0) = make_longlong2(ra[0], ra[1]);
+          *reinterpret_cast<longlong2*>(arow + f0 + 2) = make_longlong2(ra[2], ra[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (f0 + q < p.F) arow[f0 + q] = ra[q];
+        }
       }
     }
   }
@@ -425,7 +501,8 @@ static int launch_seg(const SegParams& p, cudaStream_t s) {
     segreduce_kernel<T, VB, RED, ARG, HAS_W, U><<<(unsigned)blocks, kSegThreads, 0, s>>>(p);
     GNO_LAUNCHED("segreduce_kernel");
   }
-  const int64_t total = p.n_span * p.F + (p.accumulate ? 0 : p.n_empty * p.F);
+  const int64_t quads = (p.F + 3) / 4;
+  const int64_t total = p.n_span * quads + (p.accumulate ? 0 : p.n_empty * quads);
   if (total > 0) {
     const int grid = (int)imin64(ceil_div(total, 256), (int64_t)kNumSMs * 16);
     segfinish_kernel<T, RED, ARG><<<grid, 256, 0, s>>>(p);
@@ -485,8 +562,9 @@ int gno_segment_reduce_workspace(const gno_csr* g, int64_t F, int dtype, int red
   WorkspaceSizer sz;
   const int64_t n_chunks = ceil_div(g->E, g->chunk_len);
   if (n_chunks > 0) {
-    sz.take<float>((size_t)(2 * n_chunks * F));
-    if (reduce == GNO_MIN || reduce == GNO_MAX) sz.take<int32_t>((size_t)(2 * n_chunks * F));
+    const int64_t Fp = (F + 7) / 8 * 8;
+    sz.take<float>((size_t)(2 * n_chunks * Fp));
+    if (reduce == GNO_MIN || reduce == GNO_MAX) sz.take<int32_t>((size_t)(2 * n_chunks * Fp));
   }
   *bytes = sz.total();
   return GNO_OK;
@@ -522,11 +600,15 @@ int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows, int64_t 
   const int es = dtype_size(dtype);
   GNO_CHECK_ARG((((uintptr_t)x | (uintptr_t)out) % es) == 0,
                 "gno_segment_reduce: buffers not aligned to the element size");
-  // Widest vector every row start and the row length allow.
-  const uintptr_t a = (uintptr_t)x | (uintptr_t)out | (uintptr_t)(ldx * es) | (uintptr_t)(ldo * es) |
-                      (uintptr_t)(F * es);
+  // Widest gather vector the row starts of x allow.  A row whose length is not a multiple of it
+  // is still read with full vectors when the row stride leaves room for the over-read (x padded
+  // by the caller, e.g. F=602: 1204-byte bf16 rows stored with a 1216-byte stride); the extra
+  // columns are dropped on output.
+  const uintptr_t ax = (uintptr_t)x | (uintptr_t)(ldx * es);
   int vb = 16;
-  while (vb > es && (a % vb) != 0) vb >>= 1;
+  while (vb > es && (ax % vb) != 0) vb >>= 1;
+  while (vb > es && (F * es) % vb != 0 && ceil_div(F * es, vb) * vb > ldx * es) vb >>= 1;
+  const uintptr_t ao = (uintptr_t)out | (uintptr_t)(ldo * es) | (uintptr_t)(F * es);
 
   SegParams p;
   p.gidx = g->gidx;
@@ -546,10 +628,12 @@ int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows, int64_t 
   p.n_span = g->n_span;
   p.n_empty = g->n_empty;
   p.F = F;
+  p.Fp = (F + 7) / 8 * 8;
+  p.vec_out = (ao % vb) == 0;
   p.ldx_bytes = ldx * es;
   p.ldo_bytes = ldo * es;
   p.arg_fill = arg_fill;
-  p.nvec = (int)(F * es / vb);
+  p.nvec = (int)ceil_div(F * es, vb);
   p.ncoltiles = (p.nvec + 31) / 32;
   int G = 1;
   while (G < p.nvec && G < 32) G <<= 1;
@@ -561,9 +645,9 @@ int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows, int64_t 
   if (p.n_chunks > 0) {
     if (wsp == nullptr) return fail(GNO_ERR_WORKSPACE, "gno_segment_reduce: workspace is NULL");
     Workspace ws(wsp, ws_bytes);
-    p.part_val = ws.take<float>((size_t)(2 * p.n_chunks * F));
+    p.part_val = ws.take<float>((size_t)(2 * p.n_chunks * p.Fp));
     if (reduce == GNO_MIN || reduce == GNO_MAX)
-      p.part_arg = ws.take<int32_t>((size_t)(2 * p.n_chunks * F));
+      p.part_arg = ws.take<int32_t>((size_t)(2 * p.n_chunks * p.Fp));
     if (!ws.ok())
       return fail(GNO_ERR_WORKSPACE, "gno_segment_reduce: workspace too small (%zu < %zu)", ws_bytes, ws.off);
   }

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "gno_segment_reduce_lastdim": (c_int, [POINTER(gno_csr), c_void_p, c_int64, c_int64, c_int64,
                                            c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
                                            c_int, c_void_p]),
+    "gno_pad_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "gno_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p,
                                 c_void_p]),
     "gno_scatter_elementwise_workspace": (c_int, [c_int64, c_int64, c_int64, c_int, c_int,

@@ -1,0 +1,106 @@
+"""Destination-partitioned aggregation across the GPUs of one box.
+
+Destination rows are independent, so they are split into P contiguous ranges, chosen so every
+rank gets about the same number of EDGES (power-law graphs concentrate edges on few rows).  Rank r
+holds the dst-sorted edge shard of its range, the feature rows of its range, and produces the
+output rows of its range.  The one exchange step is an all-gather of the feature shards (NCCL
+over NVLink via torch.distributed; gloo in the CPU tests); outputs stay partitioned.
+
+Shards may have different row counts; NCCL all-gather wants equal pieces, so every shard is padded
+to `max_rows` and global source ids are remapped once, at plan time, to rows of the padded
+[P * max_rows, F] gather buffer.  The partition / remap / exchange logic is device-agnostic torch
+(tested with gloo, world_size 2, on CPU); only `aggregate` needs the CUDA library.
+"""
+import torch
+import torch.distributed as dist
+
+
+def edge_balanced_ranges(row_counts, world):
+    """Split rows [0, N) into `world` contiguous ranges with ~equal edge counts.
+
+    row_counts: int64 [N] edges per destination row.  Returns int64 [world + 1] boundaries."""
+    n = row_counts.numel()
+    csum = torch.cumsum(row_counts.to(torch.int64), 0)
+    total = int(csum[-1]) if n else 0
+    targets = torch.arange(1, world, dtype=torch.float64, device=row_counts.device) * (total / world)
+    cuts = torch.searchsorted(csum.to(torch.float64), targets, right=False) + 1 if n else \
+        torch.zeros(world - 1, dtype=torch.int64)
+    cuts = cuts.clamp_(max=n).to(torch.int64)
+    bounds = torch.cat([torch.zeros(1, dtype=torch.int64, device=cuts.device), cuts,
+                        torch.full((1,), n, dtype=torch.int64, device=cuts.device)])
+    return torch.cummax(bounds, 0).values  # monotone even for degenerate inputs
+
+
+def partition_graph(src, dst, num_nodes, world):
+    """Split a global edge list into per-rank shards by destination range.
+
+    Returns (bounds [world+1], [(src_global_r, dst_local_r) for r in range(world)])."""
+    counts = torch.bincount(dst, minlength=num_nodes)
+    bounds = edge_balanced_ranges(counts, world)
+    owner = torch.searchsorted(bounds[1:].contiguous(), dst, right=True)
+    shards = []
+    for r in range(world):
+        m = owner == r
+        shards.append((src[m], dst[m] - bounds[r]))
+    return bounds, shards
+
+
+class DistAggregator:
+    """One rank's half of the partitioned aggregation.
+
+    bounds      int64 [P+1] row boundaries (same on every rank)
+    src_global  int64 [E_r]  global source node of each local edge
+    dst_local   int64 [E_r]  destination row inside this rank's range
+    """
+
+    def __init__(self, bounds, src_global, dst_local, rank=None, world=None, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.bounds = bounds.to(torch.int64).cpu()
+        rows = self.bounds[1:] - self.bounds[:-1]
+        self.n_local = int(rows[self.rank])
+        self.max_rows = int(rows.max())
+        self.dst_local = dst_local
+        # global source id -> row of the padded gather buffer [P * max_rows, F]
+        b = self.bounds.to(src_global.device)
+        owner = torch.searchsorted(b[1:].contiguous(), src_global, right=True)
+        self.src_padded = owner * self.max_rows + (src_global - b[owner])
+        self._plan = None
+        self._gidx = None
+
+    # -- exchange -------------------------------------------------------------------------------
+    def exchange(self, x_local, out=None):
+        """All-gather the feature shards into the padded [P * max_rows, F] buffer."""
+        F = x_local.size(1)
+        if x_local.size(0) != self.n_local:
+            raise ValueError("x_local must hold this rank's rows")
+        if out is None:
+            out = torch.empty((self.world * self.max_rows, F), dtype=x_local.dtype, device=x_local.device)
+        if self.n_local == self.max_rows:
+            piece = x_local.contiguous()
+        else:  # pad this shard to max_rows (padding rows are never referenced)
+            piece = torch.empty((self.max_rows, F), dtype=x_local.dtype, device=x_local.device)
+            piece[:self.n_local].copy_(x_local)
+        if self.world == 1:
+            out.copy_(piece)
+            return out
+        dist.all_gather_into_tensor(out, piece, group=self.group)
+        return out
+
+    # -- local aggregation (CUDA library) -------------------------------------------------------
+    def plan(self):
+        if self._plan is None:
+            from . import plan as planmod
+            self._plan = planmod.build_plan(self.dst_local, self.n_local)
+            self._gidx = self._plan.sorted_ids(self.src_padded)
+        return self._plan, self._gidx
+
+    def aggregate(self, x_local, reduce="sum", return_arg=False, x_full=None, out=None):
+        """out[range_r] = reduce over local edges of x_global[src]; arg = local edge position."""
+        from . import ops
+        plan, gidx = self.plan()
+        xf = self.exchange(x_local, x_full)
+        want_arg = return_arg and reduce in ("min", "max")
+        return ops.segment_reduce(plan, xf, reduce, gidx=gidx, eid=plan.perm, want_arg=want_arg,
+                                  arg_fill=plan.E, out=out)

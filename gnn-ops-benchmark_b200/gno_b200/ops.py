@@ -91,6 +91,7 @@ def segment_reduce(plan, x, reduce, *, gidx=None, eid=None, weights=None, out=No
         arg_fill = plan.E
     if weights is not None:
         weights = weights.to(x.dtype).contiguous()
+    x = _pad_for_gather(x, plan)
     csr = plan.csr(gidx, eid if want_arg else None)
     nbytes = ctypes.c_size_t()
     check(lib.gno_segment_reduce_workspace(ctypes.byref(csr), F, dt, red, 1 if want_arg else 0,
@@ -103,6 +104,26 @@ def segment_reduce(plan, x, reduce, *, gidx=None, eid=None, weights=None, out=No
                                      _ptr(out), ldo, _ptr(arg), int(arg_fill), F, dt, red,
                                      1 if accumulate else 0, _ptr(ws), nbytes.value, _stream(dev)))
     return (out, arg) if want_arg else out
+
+
+def _pad_for_gather(x, plan):
+    """Rows whose byte length is not a multiple of 16 (F=602: 2408 B fp32, 1204 B bf16) would be
+    gathered with 8/4-byte loads.  When the gather volume dwarfs x (E >> rows), copy x once into a
+    scratch whose row stride is a multiple of 16 bytes; the kernel then reads whole 128-bit
+    vectors and drops the padding columns on output."""
+    es = x.element_size()
+    row_bytes = x.size(1) * es
+    if row_bytes % 16 == 0 or row_bytes < 64 or plan.E_valid < 4 * x.size(0):
+        return x
+    if (x.stride(0) * es) % 16 == 0 and x.stride(0) * es >= (row_bytes + 15) // 16 * 16 \
+            and x.data_ptr() % 16 == 0:
+        return x  # caller already padded
+    ld = ((row_bytes + 15) // 16 * 16) // es
+    xp = torch.empty((x.size(0), ld), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gno_pad_rows(_ptr(x), x.size(0), row_bytes, x.stride(0) * es, _ptr(xp), ld * es,
+                               _stream(x.device)))
+    return xp[:, :x.size(1)]
 
 
 def _segment_reduce_lastdim(plan, x2d, reduce, gidx, eid, out2d, accumulate, want_arg, arg_fill):

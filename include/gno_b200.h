@@ -162,7 +162,8 @@ typedef struct gno_csr {
  * lane group), atomic-free and deterministic; fp32 accumulation for every
  * dtype, one rounding at the end.
  *
- *   x        [x_rows, F] with row stride ldx elements
+ *   x        [x_rows, F] with row stride ldx elements; x_rows*ldx elements
+ *            must be readable (a padded stride is read in whole vectors)
  *   w        [E] per-sorted-edge weights in x's dtype, or NULL (spmm value)
  *   out      [N, F] with row stride ldo elements
  *   arg      [N, F] int64 (contiguous) or NULL; MIN/MAX only.  Winner =
@@ -199,6 +200,14 @@ int gno_segment_reduce_lastdim(const gno_csr* g, const void* x, int64_t B,
                                int64_t* arg, int64_t arg_fill, int dtype,
                                int reduce, int accumulate,
                                gno_stream_t stream);
+
+/* Re-stride a row-major matrix: dst[r, :row_bytes] = src[r, :row_bytes] with
+ * independent row strides.  Used to give feature rows a 16-byte-multiple
+ * stride (F=602: 2408 B fp32 / 1204 B bf16 rows) so the gather kernel can use
+ * 128-bit loads; gno_segment_reduce reads whole vectors when ldx leaves room. */
+int gno_pad_rows(const void* src, int64_t rows, int64_t row_bytes,
+                 int64_t src_stride_bytes, void* dst, int64_t dst_stride_bytes,
+                 gno_stream_t stream);
 
 /* out[k, :] = x[index[k], :]  (row gather with 128-bit accesses): the
  * un-fused index_select of benchmark_native_index_select.py:12-15. */

@@ -1,0 +1,76 @@
+"""world_size-2 gloo tests (CPU) of the partitioned-aggregation host logic: edge-balanced
+ranges, source remapping into the padded gather buffer, the all-gather exchange.  The local
+reduction is done by the oracle here (no GPU); the CUDA path is covered by test_gpu_dist.py."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _graph(seed, N, E, F):
+    g = torch.Generator().manual_seed(seed)
+    dst = (torch.rand(E, generator=g) ** 3 * N).long().clamp_(0, N - 1)  # skewed in-degrees
+    src = torch.randint(0, N, (E,), generator=g)
+    x = (torch.randn(N, F, generator=g) * 4).round() / 4
+    return src, dst, x
+
+
+def _worker(rank, world, port, N, E, F, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gno_b200.dist import DistAggregator, partition_graph
+        src, dst, x = _graph(3, N, E, F)
+        bounds, shards = partition_graph(src, dst, N, world)
+        s_r, d_r = shards[rank]
+        agg = DistAggregator(bounds, s_r, d_r)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        x_full = agg.exchange(x[lo:hi].contiguous())
+        ok = True
+        for red in ("sum", "max", "mean"):
+            got, garg = oracle.gather_scatter(x_full, agg.src_padded, d_r, hi - lo, red)
+            want, warg = oracle.gather_scatter(x, src, dst, N, red)
+            ok &= torch.equal(got, want[lo:hi]) if red == "max" else torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-5)
+            if red == "max":
+                # arg is a position in the LOCAL shard: map back to the global edge id
+                local_to_global = torch.nonzero((dst >= lo) & (dst < hi)).flatten()
+                sentinel = garg == s_r.numel()
+                mapped = torch.where(sentinel, torch.full_like(garg, E), local_to_global[garg.clamp(max=max(s_r.numel() - 1, 0))])
+                ok &= torch.equal(mapped, warg[lo:hi])
+        ret[rank] = (bool(ok), int(d_r.numel()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_aggregation_gloo_world2():
+    world, N, E, F = 2, 301, 5000, 6
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker, args=(world, _free_port(), N, E, F, ret), nprocs=world, join=True)
+        assert all(ret[r][0] for r in range(world)), dict(ret)
+        edges = [ret[r][1] for r in range(world)]
+        assert sum(edges) == E
+        assert max(edges) < 0.65 * E, f"ranges are not edge-balanced: {edges}"
+
+
+def test_edge_balanced_ranges():
+    from gno_b200.dist import edge_balanced_ranges
+    counts = torch.tensor([100, 1, 1, 1, 1, 96, 50, 50])
+    b = edge_balanced_ranges(counts, 3)
+    assert b[0] == 0 and b[-1] == 8 and (b[1:] >= b[:-1]).all()
+    per = [int(counts[b[i]:b[i + 1]].sum()) for i in range(3)]
+    assert sum(per) == 300 and max(per) <= 200
+    assert edge_balanced_ranges(torch.zeros(0, dtype=torch.int64), 4).tolist() == [0, 0, 0, 0, 0]
+    assert edge_balanced_ranges(torch.tensor([5]), 2).tolist()[-1] == 1

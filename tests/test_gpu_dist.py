@@ -1,0 +1,58 @@
+"""Multi-GPU parity of the partitioned aggregation (NCCL all-gather + local segment reduce).
+Needs >= 2 CUDA devices (gpurun --gpus 2); skipped otherwise."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from gno_b200.dist import DistAggregator, partition_graph
+        g = torch.Generator().manual_seed(5)
+        N, E, F = 3001, 200_000, 100
+        dst = (torch.rand(E, generator=g) ** 3 * N).long().clamp_(0, N - 1)
+        src = torch.randint(0, N, (E,), generator=g)
+        x = (torch.randn(N, F, generator=g) * 4).round() / 4
+        bounds, shards = partition_graph(src, dst, N, world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        agg = DistAggregator(bounds, shards[rank][0].to(dev), shards[rank][1].to(dev))
+        ok = True
+        for red in ("sum", "max"):
+            got = agg.aggregate(x[lo:hi].to(dev), red, return_arg=True)
+            want, warg = oracle.gather_scatter(x, src, dst, N, red)
+            if red == "max":
+                ok &= torch.equal(got[0].cpu(), want[lo:hi])
+            else:
+                ok &= torch.allclose(got.cpu(), want[lo:hi], rtol=1e-5, atol=1e-3)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_aggregation_nccl():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    world = 2
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+        assert all(ret[r] for r in range(world)), dict(ret)
