@@ -42,60 +42,65 @@ __global__ void __launch_bounds__(kSortThreads)
   counts[(int64_t)t * num_tiles + blockIdx.x] = s;
 }
 
+// Shared memory of the scatter kernel (dynamic): separate key and payload
+// exchange buffers so both move with one barrier pair and nothing but the
+// ranks stays in registers across it (<= 64 registers ⇒ 4 CTAs / 32 warps per SM).
 template <typename KeyT, typename ValT, bool HAS_VAL>
-__global__ void __launch_bounds__(kSortThreads)
+struct ScatterSmem {
+  int warp_hist[kSortWarps][kRadix];
+  int digit_start[kRadix];
+  int gbase[kRadix];
+  int scan_tmp[12];
+  KeyT ex_k[kSortSub];
+  ValT ex_v[HAS_VAL ? kSortSub : 1];
+};
+
+template <typename KeyT, typename ValT, bool HAS_VAL>
+__global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 4 : 3)
     radix_scatter_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                          const ValT* __restrict__ vals_in, ValT* __restrict__ vals_out,
                          const int32_t* __restrict__ offsets, int64_t n, int shift, unsigned mask,
                          int subtiles, int64_t num_tiles) {
-  __shared__ int warp_hist[kSortWarps][kRadix];
-  __shared__ int digit_start[kRadix];
-  __shared__ int gbase[kRadix];
-  __shared__ int running[kRadix];
-  __shared__ int scan_tmp[9];
-  constexpr int kExBytes = kSortSub * (sizeof(KeyT) > sizeof(ValT) ? sizeof(KeyT) : sizeof(ValT));
-  __shared__ __align__(16) unsigned char ex_raw[kExBytes];
-  KeyT* ex_k = reinterpret_cast<KeyT*>(ex_raw);
-  ValT* ex_v = reinterpret_cast<ValT*>(ex_raw);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ScatterSmem<KeyT, ValT, HAS_VAL>& sm = *reinterpret_cast<ScatterSmem<KeyT, ValT, HAS_VAL>*>(smem_raw);
 
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
   const unsigned lt_mask = (1u << l) - 1u;
   const int64_t tile = blockIdx.x;
-  running[t] = offsets[(int64_t)t * num_tiles + tile];
+  int running = offsets[(int64_t)t * num_tiles + tile];  // thread t owns digit t
 
   for (int sub = 0; sub < subtiles; ++sub) {
     const int64_t base = (tile * subtiles + sub) * (int64_t)kSortSub;
     if (base >= n) break;
 #pragma unroll
-    for (int i = 0; i < kSortWarps; ++i) warp_hist[i][t] = 0;
+    for (int i = 0; i < kSortWarps; ++i) sm.warp_hist[i][t] = 0;
     __syncthreads();
 
     KeyT key[kSortItems];
-    ValT val[kSortItems];
     int pos[kSortItems];
     const int64_t wbase = base + (int64_t)w * (kSortItems * 32) + l;
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
       const int64_t idx = wbase + i * 32;
       key[i] = (idx < n) ? keys_in[idx] : ~KeyT(0);
-      if (HAS_VAL) {
-        if (vals_in != nullptr)
-          val[i] = (idx < n) ? vals_in[idx] : ValT(0);
-        else
-          val[i] = (ValT)idx;  // identity payload: first pass of an argsort
-      }
     }
     // Warp-level ranking: equal digits in one round get consecutive ranks in
     // lane order; rounds are ordered, so ranks follow input order.
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
       const unsigned d = (unsigned)(key[i] >> shift) & mask;
-      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      // lanes holding the same digit: 8 ballots (MATCH.ANY measured ~3x slower on sm_100a)
+      unsigned peers = 0xffffffffu;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const unsigned vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+        peers &= ((d >> b) & 1u) ? vote : ~vote;
+      }
       const int leader = __ffs(peers) - 1;
       int old = 0;
       if (l == leader) {
-        old = warp_hist[w][d];
-        warp_hist[w][d] = old + __popc(peers);
+        old = sm.warp_hist[w][d];
+        sm.warp_hist[w][d] = old + __popc(peers);
       }
       old = __shfl_sync(0xffffffffu, old, leader);
       pos[i] = old + __popc(peers & lt_mask);
@@ -106,45 +111,46 @@ __global__ void __launch_bounds__(kSortThreads)
     int sum = 0;
 #pragma unroll
     for (int i = 0; i < kSortWarps; ++i) {
-      const int c = warp_hist[i][t];
-      warp_hist[i][t] = sum;
+      const int c = sm.warp_hist[i][t];
+      sm.warp_hist[i][t] = sum;
       sum += c;
     }
     int total;
-    const int start = block_exclusive_scan_256(sum, scan_tmp, &total);
-    digit_start[t] = start;
-    gbase[t] = running[t] - start;
-    running[t] += sum;
+    const int start = block_exclusive_scan_256(sum, sm.scan_tmp, &total);
+    sm.digit_start[t] = start;
+    sm.gbase[t] = running - start;
+    running += sum;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
       const unsigned d = (unsigned)(key[i] >> shift) & mask;
-      pos[i] += digit_start[d] + warp_hist[w][d];
-      ex_k[pos[i]] = key[i];
+      pos[i] += sm.digit_start[d] + sm.warp_hist[w][d];
+      sm.ex_k[pos[i]] = key[i];
+    }
+    if (HAS_VAL) {  // payload goes straight from global to its sorted slot
+#pragma unroll
+      for (int i = 0; i < kSortItems; ++i) {
+        const int64_t idx = wbase + i * 32;
+        ValT v;
+        if (vals_in != nullptr)
+          v = (idx < n) ? vals_in[idx] : ValT(0);
+        else
+          v = (ValT)idx;  // identity payload: first pass of an argsort
+        sm.ex_v[pos[i]] = v;
+      }
     }
     __syncthreads();
     const int64_t remain = n - base;
     const int valid = remain < kSortSub ? (int)remain : kSortSub;
-    int gpos[kSortItems];
 #pragma unroll
     for (int j = 0; j < kSortItems; ++j) {
       const int p = j * kSortThreads + t;
       if (p < valid) {
-        const KeyT k = ex_k[p];
+        const KeyT k = sm.ex_k[p];
         const unsigned d = (unsigned)(k >> shift) & mask;
-        gpos[j] = gbase[d] + p;
-        keys_out[gpos[j]] = k;
-      }
-    }
-    if (HAS_VAL) {
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < kSortItems; ++i) ex_v[pos[i]] = val[i];
-      __syncthreads();
-#pragma unroll
-      for (int j = 0; j < kSortItems; ++j) {
-        const int p = j * kSortThreads + t;
-        if (p < valid) vals_out[gpos[j]] = ex_v[p];
+        const int gpos = sm.gbase[d] + p;
+        keys_out[gpos] = k;
+        if (HAS_VAL) vals_out[gpos] = sm.ex_v[p];
       }
     }
     __syncthreads();
@@ -201,6 +207,11 @@ static int sort_impl(const KeyT* keys_in, KeyT* keys_out, const ValT* vals_in, V
     return fail(GNO_ERR_WORKSPACE, "gno_sort_pairs: workspace too small (%zu < %zu)", ws_bytes, ws.off);
 
   const int passes = (end_bit - begin_bit + 7) / 8;
+  const size_t smem_bytes = sizeof(ScatterSmem<KeyT, ValT, HAS_VAL>);
+  if (smem_bytes > 48 * 1024) {
+    GNO_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ValT, HAS_VAL>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  }
   if (passes == 0) {
     const int grid = (int)gno::imin64(ceil_div(n, 256), (int64_t)kNumSMs * 16);
     copy_kernel<KeyT><<<grid, 256, 0, s>>>(keys_in, keys_out, n);
@@ -229,7 +240,7 @@ static int sort_impl(const KeyT* keys_in, KeyT* keys_out, const ValT* vals_in, V
     GNO_LAUNCHED("radix_hist_kernel");
     int rc = exclusive_scan_i32(counts, counts, (int64_t)kRadix * g.num_tiles, scan_ws, s);
     if (rc) return rc;
-    radix_scatter_kernel<KeyT, ValT, HAS_VAL><<<(unsigned)g.num_tiles, kSortThreads, 0, s>>>(
+    radix_scatter_kernel<KeyT, ValT, HAS_VAL><<<(unsigned)g.num_tiles, kSortThreads, smem_bytes, s>>>(
         src_k, dst_k, src_v, dst_v, counts, n, shift, mask, g.subtiles, g.num_tiles);
     GNO_LAUNCHED("radix_scatter_kernel");
     src_k = dst_k;
