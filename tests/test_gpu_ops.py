@@ -343,3 +343,27 @@ def test_golden_native_ops(cuda):
     close(got, t("sadd_out"), torch.float16, t("sadd_scale"))
     got = gno_b200.scatter(t("smul_src").to(cuda), t("smul_idx").to(cuda), -1, None, t("smul_src").shape[-1], "mul")
     close(got, t("smul_out"), torch.float32)
+
+
+# ---- host-buffer API (the e2e path of bench.py) -------------------------------------------------
+def test_host_api_and_pipeline(cuda):
+    from gno_b200.host import HostPipeline, gather_scatter_host
+    g = torch.Generator().manual_seed(77)
+    N, E, F = 4000, 150_000, 100
+    x = torch.randn(N, F, generator=g).pin_memory()
+    ei = torch.stack([torch.randint(0, N, (E,), generator=g),
+                      (torch.rand(E, generator=g) ** 3 * N).long().clamp_(0, N - 1)]).pin_memory()
+    want, _ = oracle.gather_scatter(x, ei[0], ei[1], N, "sum")
+    scale = oracle.gather_scatter(x.abs(), ei[0], ei[1], N, "sum")[0]
+    got = gather_scatter_host(x, ei, N, "sum")
+    assert not got.is_cuda
+    close(got, want, torch.float32, scale)
+    pipe = HostPipeline(N, "sum")
+    outs = []
+    pipe.submit(x, ei)
+    for _ in range(3):
+        pipe.submit(x, ei)
+        outs.append(pipe.result())
+    outs.append(pipe.result())
+    for o in outs:
+        assert torch.equal(o, got), "pipelined results must be bit-identical (deterministic kernels)"
