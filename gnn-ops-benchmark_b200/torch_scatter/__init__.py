@@ -12,45 +12,58 @@ from typing import Optional, Tuple
 
 import torch
 
+from gno_b200 import autograd as _ag
 from gno_b200 import ops as _ops
+from gno_b200 import torch_ops as _torch_ops
 
 __version__ = "2.0.9+gno.b200"
+
+_torch_ops.register()  # torch.ops.torch_scatter.* for TorchScript callers
+
+
+def _scatter(src, index, dim, out, dim_size, reduce, return_arg=False):
+    if out is None and src.requires_grad and torch.is_grad_enabled():
+        r = _ag.scatter(src, index, dim, dim_size, reduce)
+        if reduce in ("min", "max") and not return_arg:
+            return r[0]
+        return r
+    return _ops.scatter(src, index, dim, out, dim_size, reduce, return_arg=return_arg)
 
 
 def scatter_sum(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
                 out: Optional[torch.Tensor] = None,
                 dim_size: Optional[int] = None) -> torch.Tensor:
-    return _ops.scatter(src, index, dim, out, dim_size, "sum")
+    return _scatter(src, index, dim, out, dim_size, "sum")
 
 
 def scatter_add(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
                 out: Optional[torch.Tensor] = None,
                 dim_size: Optional[int] = None) -> torch.Tensor:
-    return _ops.scatter(src, index, dim, out, dim_size, "sum")
+    return _scatter(src, index, dim, out, dim_size, "sum")
 
 
 def scatter_mul(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
                 out: Optional[torch.Tensor] = None,
                 dim_size: Optional[int] = None) -> torch.Tensor:
-    return _ops.scatter(src, index, dim, out, dim_size, "mul")
+    return _scatter(src, index, dim, out, dim_size, "mul")
 
 
 def scatter_mean(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
                  out: Optional[torch.Tensor] = None,
                  dim_size: Optional[int] = None) -> torch.Tensor:
-    return _ops.scatter(src, index, dim, out, dim_size, "mean")
+    return _scatter(src, index, dim, out, dim_size, "mean")
 
 
 def scatter_min(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
                 out: Optional[torch.Tensor] = None,
                 dim_size: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    return _ops.scatter(src, index, dim, out, dim_size, "min", return_arg=True)
+    return _scatter(src, index, dim, out, dim_size, "min", return_arg=True)
 
 
 def scatter_max(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
                 out: Optional[torch.Tensor] = None,
                 dim_size: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    return _ops.scatter(src, index, dim, out, dim_size, "max", return_arg=True)
+    return _scatter(src, index, dim, out, dim_size, "max", return_arg=True)
 
 
 def scatter(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
@@ -63,9 +76,9 @@ def scatter(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
     if reduce == "mean":
         return scatter_mean(src, index, dim, out, dim_size)
     if reduce == "min":
-        return _ops.scatter(src, index, dim, out, dim_size, "min")
+        return _scatter(src, index, dim, out, dim_size, "min")
     if reduce == "max":
-        return _ops.scatter(src, index, dim, out, dim_size, "max")
+        return _scatter(src, index, dim, out, dim_size, "max")
     raise ValueError
 
 

@@ -10,6 +10,9 @@ from typing import Optional, Tuple
 import torch
 
 from gno_b200 import ops as _ops
+from gno_b200 import torch_ops as _torch_ops
+
+_torch_ops.register()  # torch.ops.torch_sparse.* for TorchScript callers
 
 __version__ = "0.6.12+gno.b200"
 

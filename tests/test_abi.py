@@ -79,3 +79,17 @@ def test_product_does_not_import_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert "oracle" not in open(os.path.join(d, f)).read().lower(), os.path.join(d, f)
+
+
+def test_dispatcher_registrations_exist():
+    """torch.ops.torch_scatter.* / torch.ops.torch_sparse.* carry the upstream schemas."""
+    import torch_scatter  # noqa: F401
+    import torch_sparse  # noqa: F401
+    s = torch.ops.torch_scatter.scatter_max.default._schema
+    assert [a.name for a in s.arguments] == ["src", "index", "dim", "optional_out", "dim_size"]
+    assert len(s.returns) == 2
+    for name in ("scatter_sum", "scatter_mul", "scatter_mean", "scatter_min", "segment_sum_csr",
+                 "segment_max_csr", "gather_csr"):
+        assert hasattr(torch.ops.torch_scatter, name)
+    for name in ("spmm_sum", "spmm_mean", "spmm_min", "spmm_max", "ind2ptr", "ptr2ind"):
+        assert hasattr(torch.ops.torch_sparse, name)
