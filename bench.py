@@ -171,7 +171,7 @@ def run_reference(args):
                                    "2.0.9 scatter_sum executes)"},
         "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_json(line)
 
 
 def run_ours(args):
@@ -203,8 +203,11 @@ def run_ours(args):
     if world > 1:
         from gno_b200.dist import DistAggregator
         bounds = torch.arange(world + 1, dtype=torch.int64) * n_local
-        agg = DistAggregator(bounds, src, dst, rank=rank, world=world)
+        agg = DistAggregator(bounds, src, dst, rank=rank, world=world, stages=args.stages)
         plan, gidx = agg.plan()
+        if args.stages > 1:
+            agg.stage_plans()
+            stage_bufs = [torch.empty(world * r, F, device=dev, dtype=dtype) for r in agg.stage_rows]
     else:
         plan = planmod.build_plan(dst, n_local)
         gidx = plan.sorted_ids(src)
@@ -214,7 +217,8 @@ def run_ours(args):
 
     def step():
         if world > 1:  # NCCL all-gather of the feature shards, then the local gather-reduce
-            agg.aggregate(x_local, "sum", x_full=x_full, out=out)
+            agg.aggregate(x_local, "sum", x_full=x_full, out=out,
+                          stage_bufs=stage_bufs if args.stages > 1 else None)
         else:
             gno_b200.segment_reduce(plan, x_full, "sum", gidx=gidx, out=out)
 
@@ -349,7 +353,8 @@ def run_ours(args):
                        "plan_build_ms": plan_ms, "max_row_len": plan.max_len,
                        "chunk_len": plan.chunk_len, "rows_cut_by_chunks": plan.n_span,
                        "empty_rows": plan.n_empty,
-                       "parallelism": f"dst-partitioned x{world}, NCCL all-gather of x" if world > 1 else "single GPU"},
+                       "parallelism": (f"dst-partitioned x{world}, NCCL all-gather of x, {args.stages}-stage "
+                                       "pipelined exchange") if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -358,19 +363,42 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit_json(line):
+    """The one JSON line goes to the real stdout; everything else (NCCL banners, warnings
+    from libraries that print to fd 1) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="products", choices=sorted(WORKLOADS))
+    ap.add_argument("--stages", type=int, default=0,
+                    help="exchange pipeline depth at N>1 (default 1: measured on 2 and 4 B200s the "
+                         "staged exchange is slower than all-gather-then-reduce, see DESIGN.md §5)")
     args = ap.parse_args()
+    if args.stages <= 0:
+        args.stages = 1
     if args.impl == "reference":
         run_reference(args)
     else:

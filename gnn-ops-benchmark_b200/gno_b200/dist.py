@@ -51,9 +51,13 @@ class DistAggregator:
     bounds      int64 [P+1] row boundaries (same on every rank)
     src_global  int64 [E_r]  global source node of each local edge
     dst_local   int64 [E_r]  destination row inside this rank's range
+    stages      K > 1 pipelines the exchange (sum / mean): every shard is cut into K row chunks,
+                chunk c of all shards is all-gathered while the edges whose sources lie in chunk
+                c-1 are being aggregated (accumulating into the output), so NVLink time hides
+                behind HBM time instead of adding to it.
     """
 
-    def __init__(self, bounds, src_global, dst_local, rank=None, world=None, group=None):
+    def __init__(self, bounds, src_global, dst_local, rank=None, world=None, group=None, stages=1):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -62,31 +66,65 @@ class DistAggregator:
         self.n_local = int(rows[self.rank])
         self.max_rows = int(rows.max())
         self.dst_local = dst_local
-        # global source id -> row of the padded gather buffer [P * max_rows, F]
+        self.stages = max(1, min(int(stages), max(self.max_rows, 1)))
+        # global source id -> (owner rank, row inside the owner's shard)
         b = self.bounds.to(src_global.device)
         owner = torch.searchsorted(b[1:].contiguous(), src_global, right=True)
-        self.src_padded = owner * self.max_rows + (src_global - b[owner])
+        local = src_global - b[owner]
+        # single-stage layout: row of the padded gather buffer [P * max_rows, F]
+        self.src_padded = owner * self.max_rows + local
+        # K-stage layout: chunk c holds rows [c*mc, c*mc + rows_c) of every shard
+        self.mc = -(-self.max_rows // self.stages) if self.max_rows else 1
+        self.stage_rows = [max(0, min(self.mc, self.max_rows - c * self.mc)) for c in range(self.stages)]
+        if self.stages > 1:
+            st = torch.div(local, self.mc, rounding_mode="floor")
+            self.stage_edges = []
+            for c in range(self.stages):
+                m = st == c
+                ids = owner[m] * self.stage_rows[c] + (local[m] - c * self.mc)
+                self.stage_edges.append((ids, dst_local[m]))
         self._plan = None
         self._gidx = None
+        self._stage_plans = None
 
     # -- exchange -------------------------------------------------------------------------------
+    def _padded(self, x_local):
+        if x_local.size(0) != self.n_local:
+            raise ValueError("x_local must hold this rank's rows")
+        if self.n_local == self.max_rows:
+            return x_local.contiguous()
+        piece = torch.empty((self.max_rows, x_local.size(1)), dtype=x_local.dtype, device=x_local.device)
+        piece[:self.n_local].copy_(x_local)  # padding rows are never referenced
+        return piece
+
     def exchange(self, x_local, out=None):
         """All-gather the feature shards into the padded [P * max_rows, F] buffer."""
         F = x_local.size(1)
-        if x_local.size(0) != self.n_local:
-            raise ValueError("x_local must hold this rank's rows")
+        piece = self._padded(x_local)
         if out is None:
             out = torch.empty((self.world * self.max_rows, F), dtype=x_local.dtype, device=x_local.device)
-        if self.n_local == self.max_rows:
-            piece = x_local.contiguous()
-        else:  # pad this shard to max_rows (padding rows are never referenced)
-            piece = torch.empty((self.max_rows, F), dtype=x_local.dtype, device=x_local.device)
-            piece[:self.n_local].copy_(x_local)
         if self.world == 1:
             out.copy_(piece)
             return out
         dist.all_gather_into_tensor(out, piece, group=self.group)
         return out
+
+    def exchange_stages(self, x_local, bufs=None):
+        """Issue the K chunk all-gathers asynchronously; returns [(buffer, work)] in stage order."""
+        F = x_local.size(1)
+        piece = self._padded(x_local)
+        res = []
+        for c in range(self.stages):
+            rows = self.stage_rows[c]
+            buf = bufs[c] if bufs is not None else torch.empty((self.world * rows, F), dtype=x_local.dtype,
+                                                               device=x_local.device)
+            chunk = piece[c * self.mc:c * self.mc + rows]
+            if self.world == 1 or rows == 0:
+                buf.copy_(chunk)
+                res.append((buf, None))
+            else:
+                res.append((buf, dist.all_gather_into_tensor(buf, chunk, group=self.group, async_op=True)))
+        return res
 
     # -- local aggregation (CUDA library) -------------------------------------------------------
     def plan(self):
@@ -96,9 +134,32 @@ class DistAggregator:
             self._gidx = self._plan.sorted_ids(self.src_padded)
         return self._plan, self._gidx
 
-    def aggregate(self, x_local, reduce="sum", return_arg=False, x_full=None, out=None):
+    def stage_plans(self):
+        if self._stage_plans is None:
+            from . import plan as planmod
+            self._stage_plans = []
+            for ids, d in self.stage_edges:
+                p = planmod.build_plan(d, self.n_local)
+                self._stage_plans.append((p, p.sorted_ids(ids)))
+        return self._stage_plans
+
+    def aggregate(self, x_local, reduce="sum", return_arg=False, x_full=None, out=None, stage_bufs=None):
         """out[range_r] = reduce over local edges of x_global[src]; arg = local edge position."""
         from . import ops
+        if self.stages > 1 and reduce in ("sum", "mean") and not return_arg:
+            plans = self.stage_plans()
+            if out is None:
+                out = torch.empty((self.n_local, x_local.size(1)), dtype=x_local.dtype, device=x_local.device)
+            pending = self.exchange_stages(x_local, stage_bufs)
+            for c, ((buf, work), (p, gidx)) in enumerate(zip(pending, plans)):
+                if work is not None:
+                    work.wait()  # stream-level wait: later chunks keep flowing over NVLink
+                ops.segment_reduce(p, buf, "sum", gidx=gidx, out=out, accumulate=c > 0)
+            if reduce == "mean":
+                plan, _ = self.plan()
+                cnt = (plan.rowptr[1:] - plan.rowptr[:-1]).clamp_(min=1).to(out.dtype)
+                out.div_(cnt.view(-1, 1))
+            return out
         plan, gidx = self.plan()
         xf = self.exchange(x_local, x_full)
         want_arg = return_arg and reduce in ("min", "max")

@@ -49,6 +49,16 @@ def _worker(rank, world, port, N, E, F, ret):
                 sentinel = garg == s_r.numel()
                 mapped = torch.where(sentinel, torch.full_like(garg, E), local_to_global[garg.clamp(max=max(s_r.numel() - 1, 0))])
                 ok &= torch.equal(mapped, warg[lo:hi])
+        # K-stage pipelined layout: per-stage chunk all-gathers + per-stage edge shards sum to the same
+        agg3 = DistAggregator(bounds, s_r, d_r, stages=3)
+        total = torch.zeros(hi - lo, F)
+        for (buf, work), (ids, d_s) in zip(agg3.exchange_stages(x[lo:hi].contiguous()), agg3.stage_edges):
+            if work is not None:
+                work.wait()
+            total += oracle.gather_scatter(buf, ids, d_s, hi - lo, "sum")[0]
+        want, _ = oracle.gather_scatter(x, src, dst, N, "sum")
+        ok &= torch.allclose(total, want[lo:hi], rtol=1e-5, atol=1e-4)
+        ok &= sum(e[0].numel() for e in agg3.stage_edges) == s_r.numel()
         ret[rank] = (bool(ok), int(d_r.numel()))
     finally:
         dist.destroy_process_group()

@@ -43,6 +43,12 @@ def _worker(rank, world, port, ret):
                 ok &= torch.equal(got[0].cpu(), want[lo:hi])
             else:
                 ok &= torch.allclose(got.cpu(), want[lo:hi], rtol=1e-5, atol=1e-3)
+        # pipelined exchange (3 stages): same sums, NVLink overlapped with the gather-reduce
+        agg3 = DistAggregator(bounds, shards[rank][0].to(dev), shards[rank][1].to(dev), stages=3)
+        for red in ("sum", "mean"):
+            got = agg3.aggregate(x[lo:hi].to(dev), red)
+            want, _ = oracle.gather_scatter(x, src, dst, N, red)
+            ok &= torch.allclose(got.cpu(), want[lo:hi], rtol=1e-5, atol=1e-3)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
