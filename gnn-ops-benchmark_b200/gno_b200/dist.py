@@ -48,7 +48,8 @@ def partition_graph(src, dst, num_nodes, world):
 class DistAggregator:
     """One rank's half of the partitioned aggregation.
 
-    bounds      int64 [P+1] row boundaries (same on every rank)
+    bounds      int64 [P+1] destination-row boundaries (same on every rank)
+    feature_bounds  int64 [P+1] ownership of the feature rows (default: same as bounds)
     src_global  int64 [E_r]  global source node of each local edge
     dst_local   int64 [E_r]  destination row inside this rank's range
     stages      K > 1 pipelines the exchange (sum / mean): every shard is cut into K row chunks,
@@ -57,18 +58,24 @@ class DistAggregator:
                 behind HBM time instead of adding to it.
     """
 
-    def __init__(self, bounds, src_global, dst_local, rank=None, world=None, group=None, stages=1):
+    def __init__(self, bounds, src_global, dst_local, rank=None, world=None, group=None, stages=1,
+                 feature_bounds=None, exchange="allgather"):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
         self.bounds = bounds.to(torch.int64).cpu()
-        rows = self.bounds[1:] - self.bounds[:-1]
+        self.n_out = int(self.bounds[self.rank + 1] - self.bounds[self.rank])
+        # Feature rows may be owned in different ranges than the outputs: edge-balanced
+        # destination ranges of a skewed graph have very unequal row counts, and padding every
+        # feature shard to the largest would inflate the all-gather; equal feature blocks do not.
+        self.xbounds = self.bounds if feature_bounds is None else feature_bounds.to(torch.int64).cpu()
+        rows = self.xbounds[1:] - self.xbounds[:-1]
         self.n_local = int(rows[self.rank])
         self.max_rows = int(rows.max())
         self.dst_local = dst_local
         self.stages = max(1, min(int(stages), max(self.max_rows, 1)))
         # global source id -> (owner rank, row inside the owner's shard)
-        b = self.bounds.to(src_global.device)
+        b = self.xbounds.to(src_global.device)
         owner = torch.searchsorted(b[1:].contiguous(), src_global, right=True)
         local = src_global - b[owner]
         # single-stage layout: row of the padded gather buffer [P * max_rows, F]
@@ -86,6 +93,50 @@ class DistAggregator:
         self._plan = None
         self._gidx = None
         self._stage_plans = None
+        self.exchange_mode = exchange
+        if exchange == "needed":
+            self._setup_needed(src_global, owner, local)
+        elif exchange != "allgather":
+            raise ValueError("exchange must be 'allgather' or 'needed'")
+
+    # -- needed-rows-only exchange -------------------------------------------
+    def _setup_needed(self, src_global, owner, local):
+        """Skewed graphs reference only a fraction of the feature rows from each rank (RMAT-26 at
+        P=4: 26 %).  Each rank asks every owner for exactly the rows its edges read; per call the
+        owners gather those rows and one all-to-all delivers them, already in the order of the
+        sorted distinct source ids, so the gather index is just the rank of the id."""
+        uniq, inv = torch.unique(src_global, return_inverse=True)  # ascending => grouped by owner
+        b = self.xbounds.to(src_global.device)
+        uowner = torch.searchsorted(b[1:].contiguous(), uniq, right=True)
+        recv_counts = torch.bincount(uowner, minlength=self.world)
+        req = uniq - b[uowner]
+        if self.world > 1:
+            send_counts = torch.empty_like(recv_counts)
+            dist.all_to_all_single(send_counts, recv_counts, group=self.group)
+            self.send_splits = [int(v) for v in send_counts.tolist()]
+            self.recv_splits = [int(v) for v in recv_counts.tolist()]
+            serve = torch.empty(sum(self.send_splits), dtype=torch.int64, device=req.device)
+            dist.all_to_all_single(serve, req, self.send_splits, self.recv_splits, group=self.group)
+        else:
+            self.send_splits = self.recv_splits = [int(uniq.numel())]
+            serve = req
+        self.serve_rows = serve          # local rows this rank sends, grouped by requester
+        self.n_needed = int(uniq.numel())
+        self.src_needed = inv            # per-edge row of the received buffer
+
+    def exchange_needed(self, x_local, out=None):
+        """Gather the rows other ranks asked for and deliver them with one all-to-all."""
+        from . import ops
+        if x_local.size(0) != self.n_local:
+            raise ValueError("x_local must hold this rank's rows")
+        send = ops.index_select(x_local, 0, self.serve_rows) if x_local.is_cuda else \
+            x_local.index_select(0, self.serve_rows)
+        if self.world == 1:
+            return send
+        if out is None:
+            out = torch.empty((self.n_needed, x_local.size(1)), dtype=x_local.dtype, device=x_local.device)
+        dist.all_to_all_single(out, send, self.recv_splits, self.send_splits, group=self.group)
+        return out
 
     # -- exchange -------------------------------------------------------------------------------
     def _padded(self, x_local):
@@ -130,8 +181,9 @@ class DistAggregator:
     def plan(self):
         if self._plan is None:
             from . import plan as planmod
-            self._plan = planmod.build_plan(self.dst_local, self.n_local)
-            self._gidx = self._plan.sorted_ids(self.src_padded)
+            self._plan = planmod.build_plan(self.dst_local, self.n_out)
+            ids = self.src_needed if self.exchange_mode == "needed" else self.src_padded
+            self._gidx = self._plan.sorted_ids(ids)
         return self._plan, self._gidx
 
     def stage_plans(self):
@@ -139,17 +191,18 @@ class DistAggregator:
             from . import plan as planmod
             self._stage_plans = []
             for ids, d in self.stage_edges:
-                p = planmod.build_plan(d, self.n_local)
+                p = planmod.build_plan(d, self.n_out)
                 self._stage_plans.append((p, p.sorted_ids(ids)))
         return self._stage_plans
 
     def aggregate(self, x_local, reduce="sum", return_arg=False, x_full=None, out=None, stage_bufs=None):
         """out[range_r] = reduce over local edges of x_global[src]; arg = local edge position."""
         from . import ops
-        if self.stages > 1 and reduce in ("sum", "mean") and not return_arg:
+        if self.stages > 1 and reduce in ("sum", "mean") and not return_arg and \
+                self.exchange_mode == "allgather":
             plans = self.stage_plans()
             if out is None:
-                out = torch.empty((self.n_local, x_local.size(1)), dtype=x_local.dtype, device=x_local.device)
+                out = torch.empty((self.n_out, x_local.size(1)), dtype=x_local.dtype, device=x_local.device)
             pending = self.exchange_stages(x_local, stage_bufs)
             for c, ((buf, work), (p, gidx)) in enumerate(zip(pending, plans)):
                 if work is not None:
@@ -161,7 +214,10 @@ class DistAggregator:
                 out.div_(cnt.view(-1, 1))
             return out
         plan, gidx = self.plan()
-        xf = self.exchange(x_local, x_full)
+        if self.exchange_mode == "needed":
+            xf = self.exchange_needed(x_local, x_full)
+        else:
+            xf = self.exchange(x_local, x_full)
         want_arg = return_arg and reduce in ("min", "max")
         return ops.segment_reduce(plan, xf, reduce, gidx=gidx, eid=plan.perm, want_arg=want_arg,
                                   arg_fill=plan.E, out=out)

@@ -59,6 +59,14 @@ def _worker(rank, world, port, N, E, F, ret):
         want, _ = oracle.gather_scatter(x, src, dst, N, "sum")
         ok &= torch.allclose(total, want[lo:hi], rtol=1e-5, atol=1e-4)
         ok &= sum(e[0].numel() for e in agg3.stage_edges) == s_r.numel()
+        # needed-rows-only exchange: unequal feature blocks, only referenced rows travel
+        xb = torch.tensor([0, 100, N])
+        aggn = DistAggregator(bounds, s_r, d_r, feature_bounds=xb, exchange="needed")
+        xlo, xhi = int(xb[rank]), int(xb[rank + 1])
+        recv = aggn.exchange_needed(x[xlo:xhi].contiguous())
+        ok &= recv.size(0) == torch.unique(s_r).numel()
+        got, _ = oracle.gather_scatter(recv, aggn.src_needed, d_r, hi - lo, "sum")
+        ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
         ret[rank] = (bool(ok), int(d_r.numel()))
     finally:
         dist.destroy_process_group()

@@ -49,6 +49,13 @@ def _worker(rank, world, port, ret):
             got = agg3.aggregate(x[lo:hi].to(dev), red)
             want, _ = oracle.gather_scatter(x, src, dst, N, red)
             ok &= torch.allclose(got.cpu(), want[lo:hi], rtol=1e-5, atol=1e-3)
+        # needed-rows-only exchange with equal feature blocks
+        xb = torch.tensor([0, N // 2, N])
+        aggn = DistAggregator(bounds, shards[rank][0].to(dev), shards[rank][1].to(dev), feature_bounds=xb,
+                              exchange="needed")
+        got = aggn.aggregate(x[int(xb[rank]):int(xb[rank + 1])].to(dev), "max", return_arg=True)
+        want, _ = oracle.gather_scatter(x, src, dst, N, "max")
+        ok &= torch.equal(got[0].cpu(), want[lo:hi])
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
