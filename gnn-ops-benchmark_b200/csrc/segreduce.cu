@@ -28,7 +28,7 @@ namespace gno {
 constexpr int kSegThreads = 128;
 constexpr int kSegWarps = kSegThreads / 32;
 #ifndef GNO_SEG_MINB
-#define GNO_SEG_MINB 8  // cap registers at 64: 32 resident warps per SM
+#define GNO_SEG_MINB 8  // 64 registers (32 resident warps/SM); arg-tracking and 16-bit variants get 72 (28 warps)
 #endif
 #ifndef GNO_SEG_INFLIGHT
 #define GNO_SEG_INFLIGHT 64  // bytes of gathered rows in flight per lane (sets the unroll U)
@@ -178,14 +178,14 @@ __device__ __forceinline__ float finalize(float a, int e, float prev, float cnt,
 
 // Write one finished (or partial) row segment held by a worker.
 template <typename T, int VB, int RED, bool ARG>
-__device__ __forceinline__ void flush_row(const SegParams& p, int64_t row, int64_t chunk, bool head,
-                                          bool tail, int64_t seg_len, int v,
+__device__ __forceinline__ void flush_row(const SegParams& p, int row, int chunk, bool head,
+                                          bool tail, int seg_len, int v,
                                           const float (&acc)[VB / (int)sizeof(T)],
                                           const int (&ae)[ARG ? VB / (int)sizeof(T) : 1]) {
   constexpr int EPV = VB / (int)sizeof(T);
   if (head || tail) {
     // a chunk that lies entirely inside one row is both: it uses the head slot
-    const int64_t slot = 2 * chunk + (head ? 0 : 1);
+    const int64_t slot = 2 * (int64_t)chunk + (head ? 0 : 1);
     float* pv = p.part_val + slot * p.Fp + (int64_t)v * EPV;
 #pragma unroll
     for (int i = 0; i < EPV; ++i) pv[i] = acc[i];
@@ -196,9 +196,9 @@ __device__ __forceinline__ void flush_row(const SegParams& p, int64_t row, int64
     }
     return;
   }
-  const float cnt = p.mean ? (float)imax64(seg_len, 1) : 0.f;
+  const float cnt = p.mean ? (float)(seg_len > 1 ? seg_len : 1) : 0.f;
   if (p.vec_out) {
-    char* optr = static_cast<char*>(p.out) + row * p.ldo_bytes + (int64_t)v * VB;
+    char* optr = static_cast<char*>(p.out) + (int64_t)row * p.ldo_bytes + (int64_t)v * VB;
     Words<VB> prev;
     if (p.accumulate) prev = ld_vec<VB>(optr);
     Words<VB> o;
@@ -207,7 +207,7 @@ __device__ __forceinline__ void flush_row(const SegParams& p, int64_t row, int64
       int64_t* ap = nullptr;
       int e = kNoArg;
       if constexpr (ARG) {
-        if (p.arg) ap = p.arg + row * p.F + (int64_t)v * EPV + i;
+        if (p.arg) ap = p.arg + (int64_t)row * p.F + (int64_t)v * EPV + i;
         e = ae[i];
       }
       const float pf = p.accumulate ? elem<T, VB>(prev, i) : 0.f;
@@ -217,7 +217,7 @@ __device__ __forceinline__ void flush_row(const SegParams& p, int64_t row, int64
   } else {
     // rows gathered with vectors wider than the output alignment (padded x): element stores,
     // dropping the padding columns.  Rare relative to the gathers.
-    T* orow = reinterpret_cast<T*>(static_cast<char*>(p.out) + row * p.ldo_bytes);
+    T* orow = reinterpret_cast<T*>(static_cast<char*>(p.out) + (int64_t)row * p.ldo_bytes);
 #pragma unroll
     for (int i = 0; i < EPV; ++i) {
       const int64_t col = (int64_t)v * EPV + i;
@@ -225,7 +225,7 @@ __device__ __forceinline__ void flush_row(const SegParams& p, int64_t row, int64
         int64_t* ap = nullptr;
         int e = kNoArg;
         if constexpr (ARG) {
-          if (p.arg) ap = p.arg + row * p.F + col;
+          if (p.arg) ap = p.arg + (int64_t)row * p.F + col;
           e = ae[i];
         }
         const float pf = p.accumulate ? DType<T>::to_f(orow[col]) : 0.f;
@@ -259,7 +259,8 @@ __device__ __forceinline__ void accumulate(float (&acc)[VB / (int)sizeof(T)],
 }
 
 template <typename T, int VB, int RED, bool ARG, bool HAS_W, int U>
-__global__ void __launch_bounds__(kSegThreads, kSegMinBlocks) segreduce_kernel(const SegParams p) {
+__global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMinBlocks - 1 : kSegMinBlocks)
+    segreduce_kernel(const SegParams p) {
   constexpr int EPV = VB / (int)sizeof(T);
   const int lane = threadIdx.x & 31;
   const int G = p.G;
@@ -267,11 +268,12 @@ __global__ void __launch_bounds__(kSegThreads, kSegMinBlocks) segreduce_kernel(c
   const int gbase = lane - li;
   const int64_t warp = (int64_t)blockIdx.x * kSegWarps + (threadIdx.x >> 5);
   const int64_t wk = warp * (32 / G) + lane / G;
-  const int64_t chunk = wk / p.ncoltiles;
-  const int ct = (int)(wk - chunk * p.ncoltiles);
+  const int64_t chunk64 = wk / p.ncoltiles;
+  const int ct = (int)(wk - chunk64 * p.ncoltiles);
+  const int chunk = (int)imin64(chunk64, (int64_t)INT_MAX);
   const int C = p.chunk_len;
-  const bool active = chunk < p.n_chunks;
-  const int64_t k0 = chunk * C;
+  const bool active = chunk64 < p.n_chunks;
+  const int64_t k0 = chunk64 * C;
   const int nv = active ? (int)imin64(C, p.E - k0) : 0;  // edges in this chunk
   const int v = ct * 32 + li;
   const bool vact = active && (v < p.nvec);
@@ -316,33 +318,32 @@ __global__ void __launch_bounds__(kSegThreads, kSegMinBlocks) segreduce_kernel(c
   int my_idx, my_row, my_e;
   float my_w;
   stage(0, my_idx, my_row, my_e, my_w);
-  for (int t = 0; t < C; t += G) {
+  const int ntiles = C / G;
+  // Tiles that are full in EVERY worker of the warp take the fast loop (all of them, except in
+  // the warp that holds the last chunk); the rest go through the small generic loop below.
+  int nfull = (G >= U) ? __reduce_min_sync(0xffffffffu, nv / G) : 0;
+  int ti = 0;
+  for (; ti < nfull; ++ti) {
+    const int t = ti * G;
     // prefetch the next tile's records while this tile's rows are gathered
     int nx_idx = 0, nx_row = 0, nx_e = 0;
     float nx_w = 0.f;
-    if (t + G < C) stage(t + G, nx_idx, nx_row, nx_e, nx_w);
-    const int rem = nv - t;  // valid edges from this tile on (may be <= 0)
+    if (ti + 1 < ntiles) stage(t + G, nx_idx, nx_row, nx_e, nx_w);
     for (int j = 0; j < G; j += U) {
       Words<VB> val[U];
       int e_u[ARG ? U : 1];
       float w_u[HAS_W ? U : 1];
-      // a batch is "plain" when every slot is a real edge (U <= G and no chunk tail)
-      const bool plain = (j + U <= G) && (j + U <= rem);
+      const int lane0 = gbase + j;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int slot = j + u;
-        const int src_lane = gbase + (slot & (G - 1));
-        const int idx = __shfl_sync(0xffffffffu, my_idx, src_lane);
-        if constexpr (ARG) e_u[u] = __shfl_sync(0xffffffffu, my_e, src_lane);
-        if constexpr (HAS_W) w_u[u] = __shfl_sync(0xffffffffu, my_w, src_lane);
-        if (vact && (plain || (slot < G && slot < rem)))
-          val[u] = ld_vec<VB>(xcol + (uint64_t)((unsigned)idx) * ldx);
+        const int idx = __shfl_sync(0xffffffffu, my_idx, lane0 + u);
+        if constexpr (ARG) e_u[u] = __shfl_sync(0xffffffffu, my_e, lane0 + u);
+        if constexpr (HAS_W) w_u[u] = __shfl_sync(0xffffffffu, my_w, lane0 + u);
+        if (vact) val[u] = ld_vec<VB>(xcol + (uint64_t)((unsigned)idx) * ldx);
       }
-      // row of the batch's last edge: rows ascend, so equal to cur_row means no boundary inside
-      const int last_slot = gbase + ((j + U - 1) & (G - 1));
-      const int row_last = __shfl_sync(0xffffffffu, my_row, last_slot);
-      const bool simple = plain && (row_last == cur_row);
-      if (__all_sync(0xffffffffu, simple || !active)) {
+      // rows ascend: the batch's last row equal to cur_row means no boundary inside it
+      const int row_last = __shfl_sync(0xffffffffu, my_row, lane0 + U - 1);
+      if (__all_sync(0xffffffffu, row_last == cur_row)) {
         if (vact) {
 #pragma unroll
           for (int u = 0; u < U; ++u)
@@ -352,31 +353,66 @@ __global__ void __launch_bounds__(kSegThreads, kSegMinBlocks) segreduce_kernel(c
       } else {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int slot = j + u;
-          const int row_u = __shfl_sync(0xffffffffu, my_row, gbase + (slot & (G - 1)));
-          if (slot < G && slot < rem) {
-            if (row_u != cur_row) {  // the previous row ended inside this chunk
-              const int kk = t + slot;
-              if (vact)
-                flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, false, kk - seg_start, v, acc, ae);
-              head = false;
-              cur_row = row_u;
-              seg_start = kk;
-#pragma unroll
-              for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
-              if constexpr (ARG) {
-#pragma unroll
-                for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
-              }
-            }
+          const int row_u = __shfl_sync(0xffffffffu, my_row, lane0 + u);
+          if (row_u != cur_row) {  // the previous row ended inside this chunk
+            const int kk = t + j + u;
             if (vact)
-              accumulate<T, VB, RED, ARG, HAS_W>(acc, ae, val[u], ARG ? e_u[ARG ? u : 0] : 0,
-                                                 HAS_W ? w_u[HAS_W ? u : 0] : 0.f);
+              flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, false, kk - seg_start, v, acc, ae);
+            head = false;
+            cur_row = row_u;
+            seg_start = kk;
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
+            if constexpr (ARG) {
+#pragma unroll
+              for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
+            }
           }
+          if (vact)
+            accumulate<T, VB, RED, ARG, HAS_W>(acc, ae, val[u], ARG ? e_u[ARG ? u : 0] : 0,
+                                               HAS_W ? w_u[HAS_W ? u : 0] : 0.f);
         }
       }
     }
     my_idx = nx_idx; my_row = nx_row; my_e = nx_e; my_w = nx_w;
+  }
+  // Generic loop (chunk tails, workers narrower than a batch, idle workers of the last warp):
+  // one edge at a time — rare, so it is kept small rather than fast.
+#pragma unroll 1
+  for (; ti < ntiles; ++ti) {
+    const int t = ti * G;
+    const int rem = nv - t;  // valid edges from this tile on (may be <= 0)
+    if (__all_sync(0xffffffffu, rem <= 0)) break;
+#pragma unroll 1
+    for (int slot = 0; slot < G; ++slot) {
+      const int src_lane = gbase + slot;
+      const int idx = __shfl_sync(0xffffffffu, my_idx, src_lane);
+      const int row_u = __shfl_sync(0xffffffffu, my_row, src_lane);
+      int e1 = 0;
+      float w1 = 0.f;
+      if constexpr (ARG) e1 = __shfl_sync(0xffffffffu, my_e, src_lane);
+      if constexpr (HAS_W) w1 = __shfl_sync(0xffffffffu, my_w, src_lane);
+      if (slot < rem) {
+        Words<VB> val1;
+        if (vact) val1 = ld_vec<VB>(xcol + (uint64_t)((unsigned)idx) * ldx);
+        if (row_u != cur_row) {
+          const int kk = t + slot;
+          if (vact)
+            flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, false, kk - seg_start, v, acc, ae);
+          head = false;
+          cur_row = row_u;
+          seg_start = kk;
+#pragma unroll
+          for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
+          if constexpr (ARG) {
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
+          }
+        }
+        if (vact) accumulate<T, VB, RED, ARG, HAS_W>(acc, ae, val1, e1, w1);
+      }
+    }
+    if (ti + 1 < ntiles) stage(t + G, my_idx, my_row, my_e, my_w);
   }
   if (vact && nv > 0) {
     const bool tail = (k0 + nv < p.E) && (__ldg(erow + nv) == cur_row);
