@@ -42,7 +42,30 @@ static uint32_t enc_f_host(float f) {
 
 struct ElemShape {
   int64_t B, E, K, N;
+  int64_t KB;  // column-block width of the traversal (== K: plain row-major order)
 };
+
+// Traversal order.  With dim 0 of a wide matrix (K large) consecutive rows hit destinations
+// N*K*4 bytes apart, far beyond L2.  Visiting the elements column block by column block keeps
+// the live slice of the accumulator (N x KB x 4 bytes) L2-resident, so the atomics stay on
+// chip.  Maps the loop index j to the element's position in src / index.
+__device__ __forceinline__ int64_t elem_order(const ElemShape& sh, int64_t j) {
+  if (sh.KB >= sh.K) return j;
+  const int64_t ek = sh.E * sh.K;
+  const int64_t b = j / ek, r = j - b * ek;
+  const int64_t full = (sh.K / sh.KB) * sh.E * sh.KB;  // elements in the full-width blocks
+  int64_t e, k;
+  if (r < full) {
+    const int64_t cb = r / (sh.E * sh.KB), r2 = r - cb * sh.E * sh.KB;
+    e = r2 / sh.KB;
+    k = cb * sh.KB + (r2 - e * sh.KB);
+  } else {
+    const int64_t w = sh.K - (sh.K / sh.KB) * sh.KB, r2 = r - full;
+    e = r2 / w;
+    k = (sh.K / sh.KB) * sh.KB + (r2 - e * w);
+  }
+  return (b * sh.E + e) * sh.K + k;
+}
 
 // i over [B,E,K] → flat destination in [B,N,K] (or -1 when index is out of range)
 __device__ __forceinline__ int64_t elem_target(const ElemShape& sh, int64_t i, int64_t idx,
@@ -60,7 +83,8 @@ __global__ void __launch_bounds__(256)
     elem_add_kernel(const T* __restrict__ src, const int64_t* __restrict__ index, ElemShape sh,
                     float* __restrict__ acc, float* __restrict__ cnt) {
   const int64_t n = sh.B * sh.E * sh.K;
-  GNO_GRID_STRIDE(i, n) {
+  GNO_GRID_STRIDE(j, n) {
+    const int64_t i = elem_order(sh, j);
     int64_t e;
     const int64_t t = elem_target(sh, i, index[i], &e);
     if (t < 0) continue;
@@ -74,7 +98,8 @@ __global__ void __launch_bounds__(256)
     elem_mul_kernel(const T* __restrict__ src, const int64_t* __restrict__ index, ElemShape sh,
                     float* __restrict__ acc) {
   const int64_t n = sh.B * sh.E * sh.K;
-  GNO_GRID_STRIDE(i, n) {
+  GNO_GRID_STRIDE(j, n) {
+    const int64_t i = elem_order(sh, j);
     int64_t e;
     const int64_t t = elem_target(sh, i, index[i], &e);
     if (t < 0) continue;
@@ -107,7 +132,8 @@ __global__ void __launch_bounds__(256)
     elem_minmax_kernel(const T* __restrict__ src, const int64_t* __restrict__ index, ElemShape sh,
                        uint32_t* __restrict__ enc) {
   const int64_t n = sh.B * sh.E * sh.K;
-  GNO_GRID_STRIDE(i, n) {
+  GNO_GRID_STRIDE(j, n) {
+    const int64_t i = elem_order(sh, j);
     int64_t e;
     const int64_t t = elem_target(sh, i, index[i], &e);
     if (t < 0) continue;
@@ -124,7 +150,8 @@ __global__ void __launch_bounds__(256)
                     const uint32_t* __restrict__ enc, uint32_t enc_init,
                     long long* __restrict__ arg) {
   const int64_t n = sh.B * sh.E * sh.K;
-  GNO_GRID_STRIDE(i, n) {
+  GNO_GRID_STRIDE(j, n) {
+    const int64_t i = elem_order(sh, j);
     int64_t e;
     const int64_t t = elem_target(sh, i, index[i], &e);
     if (t < 0) continue;
@@ -241,7 +268,12 @@ int gno_scatter_elementwise(const void* src, const int64_t* index, int64_t B, in
                 "gno_scatter_elementwise: arg output only for MIN/MAX");
   if (B * N * K == 0) return GNO_OK;
   GNO_CHECK_ARG(out && (B * E * K == 0 || (src && index)), "gno_scatter_elementwise: NULL buffer");
-  ElemShape sh{B, E, K, N};
+  ElemShape sh{B, E, K, N, K};
+  // column-blocked traversal when the accumulator slice of one row-major sweep exceeds ~24 MB
+  if (K >= 64 && N * K * 4 > (int64_t(24) << 20)) {
+    int64_t kb = (int64_t(24) << 20) / (N * 4) / 32 * 32;
+    sh.KB = kb < 32 ? 32 : (kb > K ? K : kb);
+  }
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
     case GNO_F32: return scatter_elem_impl<float>((const float*)src, index, sh, (float*)out, arg, reduce, ws, ws_bytes, s);

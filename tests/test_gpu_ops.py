@@ -367,3 +367,49 @@ def test_host_api_and_pipeline(cuda):
     outs.append(pipe.result())
     for o in outs:
         assert torch.equal(o, got), "pipelined results must be bit-identical (deterministic kernels)"
+
+
+def test_cuda_graph_capture(cuda):
+    """The C-ABI never allocates or synchronises, so a warm-plan aggregation (2 launches) can be
+    captured in a CUDA graph and replayed — how launch-bound small calls (C1) should be driven."""
+    import gno_b200
+    g = torch.Generator().manual_seed(5)
+    E, N, F = 50_000, 3000, 64
+    src = torch.randn(E, F, generator=g).to(cuda)
+    idx = torch.randint(0, N, (E,), generator=g).to(cuda)
+    want = gno_b200.scatter(src, idx, 0, None, N, "sum").clone()  # builds and caches the plan
+    plan = gno_b200.plan_cache.get(idx, N)
+    out = torch.empty(N, F, device=cuda)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        gno_b200.segment_reduce(plan, src, "sum", gidx=plan.perm, out=out)  # warm-up on the side stream
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    before = gno_b200.launch_count()
+    with torch.cuda.graph(graph):
+        gno_b200.segment_reduce(plan, src, "sum", gidx=plan.perm, out=out)
+    assert gno_b200.launch_count() - before == 2
+    out.zero_()
+    src.mul_(2.0)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, gno_b200.scatter(src, idx, 0, None, N, "sum"))
+    assert torch.allclose(out, 2 * want, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("reduce", ["sum", "max", "mean"])
+def test_scatter_full_shape_column_blocked(cuda, reduce):
+    """Wide dim-0 scatter: the accumulator exceeds the L2 budget, so the kernels traverse the
+    elements column block by column block (uneven last block)."""
+    import gno_b200
+    g = torch.Generator().manual_seed(9)
+    E, K, N = 300, 4100, 1600
+    src = (torch.randn(E, K, generator=g) * 8).round() / 8
+    idx = torch.randint(0, N, (E, K), generator=g)
+    got = gno_b200.scatter(src.to(cuda), idx.to(cuda), 0, None, N, reduce, return_arg=True)
+    want, warg = oracle.scatter(src, idx, 0, N, reduce)
+    if reduce == "max":
+        assert torch.equal(got[0].cpu(), want) and torch.equal(got[1].cpu(), warg)
+    else:
+        close(got, want, torch.float32, oracle.scatter(src.abs(), idx, 0, N, reduce)[0])
