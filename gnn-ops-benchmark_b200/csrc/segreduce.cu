@@ -20,6 +20,7 @@
 // Roofline: HBM.  Algorithmic bytes per edge = F*s (feature row) + 4 (index)
 // [+4 erow, +4 eid for arg, +s weight]; per row = F*s_out [+8F arg].
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -61,6 +62,8 @@ struct SegParams {
   int mean;       // divide by max(row length, 1)
   int accumulate;
   int vec_out;    // out rows are aligned for VB-byte vector stores and F*s is a multiple of VB
+  int tma_ok;     // edge-record arrays are 16-byte aligned (bulk copies allowed)
+  int staged;     // use the TMA-staged kernel (record slab of a CTA fits the shared-memory budget)
 };
 
 template <int VB>
@@ -420,6 +423,178 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
   }
 }
 
+// ---- TMA-staged variant ------------------------------------------------------------------
+// The CTA's workers own consecutive chunks, so their edge records (destination row, gather
+// index, edge id, weight) are one contiguous slab per array.  One thread issues a 1-D bulk
+// copy (cp.async.bulk → the TMA engine, completion on an mbarrier) per array into shared
+// memory; the warps then read records with broadcast LDS instead of per-tile global loads and
+// shuffles.  No warp-synchronous operation is left in the loop, so every worker follows its own
+// row boundaries without dragging the other workers of its warp through the slow path.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+template <typename T, int VB, int RED, bool ARG, bool HAS_W, int U>
+__global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMinBlocks - 1 : kSegMinBlocks)
+    segreduce_staged_kernel(const SegParams p) {
+  constexpr int EPV = VB / (int)sizeof(T);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int G = p.G;
+  const int li = lane & (G - 1);
+  const int C = p.chunk_len;
+  const int wpc = kSegWarps * (32 / G);  // workers per CTA
+  const int64_t w0 = (int64_t)blockIdx.x * wpc;
+  const int64_t c_first = w0 / p.ncoltiles;
+  if (c_first >= p.n_chunks) return;
+  const int64_t c_last = imin64((w0 + wpc - 1) / p.ncoltiles, p.n_chunks - 1);
+  const int64_t e0 = c_first * C;
+  const int n = (int)(imin64((c_last + 1) * C, p.E) - e0);  // records staged by this CTA
+  const int cap = wpc * C;
+
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  int* s_row = reinterpret_cast<int*>(smem_raw + 128);
+  int* s_idx = s_row + cap;                       // used when p.gidx
+  int* s_e = s_idx + (p.gidx ? cap : 0);          // used when ARG and a separate eid array
+  const bool sep_e = ARG && p.eid && p.eid != p.gidx;
+  T* s_w = reinterpret_cast<T*>(s_e + (sep_e ? cap : 0));
+
+  const bool tma = p.tma_ok && (n % 8 == 0);
+  if (tma) {
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t bytes = (uint32_t)n * 4u * (1u + (p.gidx ? 1u : 0u) + (sep_e ? 1u : 0u));
+      if (HAS_W) bytes += (uint32_t)n * (uint32_t)sizeof(T);
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(s_row, p.erow + e0, (uint32_t)n * 4u, bar);
+      if (p.gidx) bulk_g2s(s_idx, p.gidx + e0, (uint32_t)n * 4u, bar);
+      if (sep_e) bulk_g2s(s_e, p.eid + e0, (uint32_t)n * 4u, bar);
+      if (HAS_W) bulk_g2s(s_w, static_cast<const T*>(p.w) + e0, (uint32_t)n * (uint32_t)sizeof(T), bar);
+    }
+    mbar_wait(bar, 0);
+  } else {  // unaligned tail slab (or unaligned caller arrays): plain cooperative copy
+    for (int i = threadIdx.x; i < n; i += kSegThreads) {
+      s_row[i] = __ldg(p.erow + e0 + i);
+      if (p.gidx) s_idx[i] = __ldg(p.gidx + e0 + i);
+      if (sep_e) s_e[i] = __ldg(p.eid + e0 + i);
+      if (HAS_W) s_w[i] = static_cast<const T*>(p.w)[e0 + i];
+    }
+    __syncthreads();
+  }
+
+  const int64_t wk = w0 + (threadIdx.x >> 5) * (32 / G) + lane / G;
+  const int64_t chunk64 = wk / p.ncoltiles;
+  if (chunk64 >= p.n_chunks) return;
+  const int ct = (int)(wk - chunk64 * p.ncoltiles);
+  const int chunk = (int)chunk64;
+  const int64_t k0 = chunk64 * C;
+  const int nv = (int)imin64(C, p.E - k0);
+  const int soff = (int)(k0 - e0);
+  const int v = ct * 32 + li;
+  const bool vact = v < p.nvec;
+  if (!vact) return;  // no warp-synchronous code below: idle lanes simply leave
+  const char* xcol = static_cast<const char*>(p.x) + (int64_t)v * VB;
+  const unsigned ldx = (unsigned)p.ldx_bytes;
+  const int* rowp = s_row + soff;
+  const int* idxp = s_idx + soff;
+  const int* ep = (sep_e ? s_e : s_idx) + soff;
+  const T* wp = s_w + soff;
+  const bool has_idx = p.gidx != nullptr;
+  const bool e_is_k = ARG && !sep_e && !(p.eid && p.eid == p.gidx);  // eid == NULL: edge id = k
+
+  float acc[EPV];
+  int ae[ARG ? EPV : 1];
+#pragma unroll
+  for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
+  if constexpr (ARG) {
+#pragma unroll
+    for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
+  }
+  int cur_row = rowp[0];
+  bool head = (k0 > 0) && (soff > 0 ? rowp[-1] : __ldg(p.erow + k0 - 1)) == cur_row;
+  int seg_start = 0;
+
+  auto close_row = [&](int new_row, int kk) {
+    flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, false, kk - seg_start, v, acc, ae);
+    head = false;
+    cur_row = new_row;
+    seg_start = kk;
+#pragma unroll
+    for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
+    if constexpr (ARG) {
+#pragma unroll
+      for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
+    }
+  };
+
+  int t = 0;
+  for (; t + U <= nv; t += U) {
+    Words<VB> val[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = has_idx ? idxp[t + u] : (int)(k0 + t + u);
+      val[u] = ld_vec<VB>(xcol + (uint64_t)((unsigned)idx) * ldx);
+    }
+    // rows ascend: the batch's last row equal to cur_row means no boundary inside it
+    const bool simple = rowp[t + U - 1] == cur_row;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!simple) {
+        const int row_u = rowp[t + u];
+        if (row_u != cur_row) close_row(row_u, t + u);
+      }
+      int e1 = 0;
+      float w1 = 0.f;
+      if constexpr (ARG) e1 = e_is_k ? (int)(k0 + t + u) : ep[t + u];
+      if constexpr (HAS_W) w1 = DType<T>::to_f(wp[t + u]);
+      accumulate<T, VB, RED, ARG, HAS_W>(acc, ae, val[u], e1, w1);
+    }
+  }
+#pragma unroll 1
+  for (; t < nv; ++t) {  // chunk tail
+    const int idx = has_idx ? idxp[t] : (int)(k0 + t);
+    const Words<VB> val1 = ld_vec<VB>(xcol + (uint64_t)((unsigned)idx) * ldx);
+    const int row_u = rowp[t];
+    if (row_u != cur_row) close_row(row_u, t);
+    int e1 = 0;
+    float w1 = 0.f;
+    if constexpr (ARG) e1 = e_is_k ? (int)(k0 + t) : ep[t];
+    if constexpr (HAS_W) w1 = DType<T>::to_f(wp[t]);
+    accumulate<T, VB, RED, ARG, HAS_W>(acc, ae, val1, e1, w1);
+  }
+  if (nv > 0) {
+    const bool tail = (k0 + nv < p.E) &&
+                      ((soff + nv < n) ? rowp[nv] : __ldg(p.erow + k0 + nv)) == cur_row;
+    flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, tail, nv - seg_start, v, acc, ae);
+  }
+}
+
 // Finish pass: (a) rows cut by a chunk boundary — combine their partials in
 // chunk order: the tail slot of the first chunk, then the head slot of every
 // later chunk; (b) empty rows — write zeros (and arg_fill).  One thread per
@@ -527,13 +702,24 @@ __global__ void __launch_bounds__(256) segfinish_kernel(const SegParams p) {
 }
 
 // ------------------------------------------------------------- dispatch --
+// Shared memory the staged kernel needs for one CTA's record slab.
+static int64_t seg_staged_bytes(const SegParams& p, int es, bool arg, bool has_w) {
+  const int64_t cap = (int64_t)kSegWarps * (32 / p.G) * p.chunk_len;
+  const bool sep_e = arg && p.eid && p.eid != p.gidx;
+  return cap * 4 * (1 + (p.gidx ? 1 : 0) + (sep_e ? 1 : 0)) + (has_w ? cap * es : 0);
+}
+
 template <typename T, int VB, int RED, bool ARG, bool HAS_W>
 static int launch_seg(const SegParams& p, cudaStream_t s) {
   constexpr int U = (GNO_SEG_INFLIGHT / VB) > 16 ? 16 : (GNO_SEG_INFLIGHT / VB);
   const int64_t workers = p.n_chunks * p.ncoltiles;
   const int64_t warps = ceil_div(workers, 32 / p.G);
   const int64_t blocks = ceil_div(warps, kSegWarps);
-  if (blocks > 0) {
+  if (blocks > 0 && p.staged) {
+    const size_t smem = 128 + (size_t)seg_staged_bytes(p, (int)sizeof(T), ARG, HAS_W);
+    segreduce_staged_kernel<T, VB, RED, ARG, HAS_W, U><<<(unsigned)blocks, kSegThreads, smem, s>>>(p);
+    GNO_LAUNCHED("segreduce_staged_kernel");
+  } else if (blocks > 0) {
     segreduce_kernel<T, VB, RED, ARG, HAS_W, U><<<(unsigned)blocks, kSegThreads, 0, s>>>(p);
     GNO_LAUNCHED("segreduce_kernel");
   }
@@ -688,6 +874,14 @@ int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows, int64_t 
       return fail(GNO_ERR_WORKSPACE, "gno_segment_reduce: workspace too small (%zu < %zu)", ws_bytes, ws.off);
   }
   const bool has_w = (w != nullptr);
+  {
+    const bool argv = (reduce == GNO_MIN || reduce == GNO_MAX);
+    const uintptr_t al = (uintptr_t)g->erow | (uintptr_t)g->gidx | (uintptr_t)(argv ? g->eid : nullptr) |
+                         (uintptr_t)w;
+    p.tma_ok = (al % 16) == 0;
+    static const int staged_env = getenv("GNO_SEG_STAGED") ? atoi(getenv("GNO_SEG_STAGED")) : 1;
+    p.staged = staged_env && seg_staged_bytes(p, es, argv, has_w) <= 24 * 1024;
+  }
   switch (dtype) {
     case GNO_F32: return dispatch_vb<float>(p, vb, reduce, with_arg, has_w, s);
     case GNO_F16: return dispatch_vb<__half>(p, vb, reduce, with_arg, has_w, s);
