@@ -358,7 +358,7 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "segreduce_kernel", "kernel_ms": k_ms,
+                         "kernel": "segreduce_staged_kernel (+ segfinish_kernel)", "kernel_ms": k_ms,
                          "algorithmic_bytes": abytes},
         }
         if cpu is not None:
