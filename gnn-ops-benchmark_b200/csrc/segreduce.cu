@@ -626,6 +626,10 @@ __global__ void __launch_bounds__(256) segfinish_kernel(const SegParams p) {
       } else {
         e[0] = e[1] = e[2] = e[3] = kNoArg;
       }
+      // Chunk partials of a hub row can number in the thousands and be nearly equal (one source
+      // feeding a hub): summing them in fp32 drifts by ~n*eps/2, so the combine runs in fp64
+      // (a few adds per output element; the chunks themselves stay fp32).
+      double ad[4] = {(double)a[0], (double)a[1], (double)a[2], (double)a[3]};
       for (int64_t c = ca + 1; c <= cb; ++c) {
         const float4 t2 = *reinterpret_cast<const float4*>(p.part_val + (2 * c) * p.Fp + f0);
         const float pv[4] = {t2.x, t2.y, t2.z, t2.w};
@@ -637,7 +641,7 @@ __global__ void __launch_bounds__(256) segfinish_kernel(const SegParams p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if constexpr (RED == GNO_SUM) {
-            a[j] += pv[j];
+            ad[j] += (double)pv[j];
           } else if constexpr (RED == GNO_MUL) {
             a[j] *= pv[j];
           } else {
@@ -649,7 +653,16 @@ __global__ void __launch_bounds__(256) segfinish_kernel(const SegParams p) {
           }
         }
       }
-      if (p.mean) cnt = (float)imax64(ke - kb, 1);
+      if constexpr (RED == GNO_SUM) {
+        if (p.mean) {
+          const double dc = (double)imax64(ke - kb, 1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ad[j] /= dc;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = (float)ad[j];
+      }
+      // (mean already applied above in fp64; cnt stays 0 so finalize does not divide again)
     } else {
       const int64_t j = i - n_a;
       const int64_t z = j / Q;
