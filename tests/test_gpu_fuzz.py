@@ -94,3 +94,46 @@ def test_fuzz_scatter_api(cuda, seed):
         got = gno_b200.scatter(src.to(cuda), index.to(cuda), dim, None, dim_size, reduce, return_arg=True)
         assert (got[0] if isinstance(got, tuple) else got).shape == want.shape, tag
         _check(got, want, warg, scale, dtype, reduce, tag)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_fuzz_sort_coalesce(cuda, seed):
+    import gno_b200
+    rnd = random.Random(200 + seed)
+    g = torch.Generator().manual_seed(200 + seed)
+    for case in range(8):
+        # radix sort: random length / bit range / key width, stability via payload
+        n = rnd.choice([0, 1, 2, 255, 4095, 4096, 4097, 33333, 262145])
+        kb = rnd.choice([4, 8])
+        bits = rnd.choice([1, 7, 8, 9, 17, 31, 32] + ([40, 63, 64] if kb == 8 else []))
+        hi = 1 << min(bits, 62)
+        keys = torch.randint(0, hi, (n,), generator=g, dtype=torch.int64)
+        if kb == 4:
+            keys = (keys & 0x7FFFFFFF).to(torch.int32)
+        vals = torch.arange(n, dtype=torch.int32)
+        k, v = gno_b200.sort_pairs(keys.to(cuda), vals.to(cuda), 0, bits)
+        ref_k, ref_p = torch.sort(keys.to(torch.int64) & ((1 << bits) - 1 if bits < 64 else -1), stable=True)
+        assert torch.equal(v.cpu().to(torch.int64), ref_p), f"sort n={n} kb={kb} bits={bits}"
+        assert torch.equal(k.cpu().to(torch.int64), keys.to(torch.int64)[ref_p])
+        # float sort along a random dim
+        shape = [rnd.choice([1, 2, 33, 257]) for _ in range(rnd.choice([1, 2, 3]))]
+        dim = rnd.randrange(len(shape))
+        x = (torch.randn(*shape, generator=g) * 2).round() / 2
+        x.view(-1)[::5] = float("nan") if rnd.random() < 0.5 else 0.0
+        desc = rnd.random() < 0.5
+        sv, si = gno_b200.sort(x.to(cuda), dim, desc)
+        wv, wi = torch.sort(x, dim=dim, descending=desc, stable=True)
+        assert torch.equal(si.cpu(), wi), f"sort_f32 shape={shape} dim={dim} desc={desc}"
+        assert torch.equal(sv.cpu().view(torch.int32), wv.view(torch.int32))
+        # coalesce / transpose
+        m, nn = rnd.choice([1, 7, 300, 70000]), rnd.choice([1, 9, 500, 1 << 20])
+        nnz = rnd.choice([1, 2, 100, 5000, 40000])
+        idx = torch.stack([torch.randint(0, m, (nnz,), generator=g), torch.randint(0, nn, (nnz,), generator=g)])
+        val = torch.rand(nnz, generator=g)
+        gi, gv = gno_b200.coalesce(idx.to(cuda), val.to(cuda), m, nn)
+        wi2, wv2 = oracle.coalesce(idx, val, m, nn)
+        assert torch.equal(gi.cpu(), wi2), f"coalesce m={m} n={nn} nnz={nnz}"
+        assert torch.allclose(gv.cpu(), wv2, rtol=1e-5, atol=1e-6)
+        ti, tv = gno_b200.transpose(gi, gv, m, nn)
+        wti, wtv = oracle.transpose(wi2, wv2, m, nn)
+        assert torch.equal(ti.cpu(), wti) and torch.equal(tv.cpu(), gv.cpu()[torch.argsort(wi2[1] * m + wi2[0])])
