@@ -116,7 +116,11 @@ def gather_csr(src: torch.Tensor, indptr: torch.Tensor,
     return _ops.gather_csr(src, indptr)
 
 
+from .composite import (scatter_log_softmax, scatter_logsumexp, scatter_softmax,  # noqa: E402
+                        scatter_std)
+
 __all__ = [
+    "scatter_std", "scatter_logsumexp", "scatter_softmax", "scatter_log_softmax",
     "scatter_sum", "scatter_add", "scatter_mul", "scatter_mean", "scatter_min", "scatter_max",
     "scatter", "segment_csr", "segment_sum_csr", "segment_add_csr", "segment_mean_csr",
     "segment_min_csr", "segment_max_csr", "gather_csr",

@@ -32,4 +32,6 @@ def spmm(index: torch.Tensor, value: torch.Tensor, m: int, n: int,
     return _ops.spmm(index, value, m, n, matrix)
 
 
-__all__ = ["coalesce", "transpose", "spmm"]
+from .tensor import SparseTensor, matmul  # noqa: E402
+
+__all__ = ["coalesce", "transpose", "spmm", "SparseTensor", "matmul"]

@@ -413,3 +413,51 @@ def test_scatter_full_shape_column_blocked(cuda, reduce):
         assert torch.equal(got[0].cpu(), want) and torch.equal(got[1].cpu(), warg)
     else:
         close(got, want, torch.float32, oracle.scatter(src.abs(), idx, 0, N, reduce)[0])
+
+
+# ---- widened surface: composites and SparseTensor ---------------------------------
+def test_scatter_composites(cuda):
+    import torch_scatter
+    g = torch.Generator().manual_seed(31)
+    src = torch.randn(500, 6, generator=g)
+    idx = torch.randint(0, 23, (500,), generator=g)
+    sm = torch_scatter.scatter_softmax(src.to(cuda), idx.to(cuda), dim=0).cpu()
+    lsm = torch_scatter.scatter_log_softmax(src.to(cuda), idx.to(cuda), dim=0).cpu()
+    lse = torch_scatter.scatter_logsumexp(src.to(cuda), idx.to(cuda), dim=0, dim_size=23).cpu()
+    std = torch_scatter.scatter_std(src.to(cuda), idx.to(cuda), dim=0, dim_size=23).cpu()
+    for i in range(23):
+        rows = (idx == i).nonzero().flatten()
+        if rows.numel() == 0:
+            continue
+        ref = torch.softmax(src[rows], dim=0)
+        assert torch.allclose(sm[rows], ref, rtol=1e-4, atol=1e-6)
+        assert torch.allclose(lsm[rows], torch.log_softmax(src[rows], dim=0), rtol=1e-4, atol=1e-5)
+        assert torch.allclose(lse[i], torch.logsumexp(src[rows], dim=0), rtol=1e-4, atol=1e-5)
+        if rows.numel() > 1:
+            assert torch.allclose(std[i], src[rows].std(dim=0), rtol=1e-3, atol=1e-4)
+
+
+def test_sparse_tensor(cuda):
+    from torch_sparse import SparseTensor, matmul
+    g = torch.Generator().manual_seed(32)
+    m, n, nnz, F = 120, 90, 3000, 24
+    ei = torch.stack([torch.randint(0, m, (nnz,), generator=g), torch.randint(0, n, (nnz,), generator=g)])
+    val = torch.rand(nnz, generator=g)
+    x = torch.randn(n, F, generator=g)
+    A = SparseTensor.from_edge_index(ei.to(cuda), val.to(cuda), sparse_sizes=(m, n))
+    ci, cv = oracle.coalesce(ei, val, m, n)
+    dense = torch.zeros(m, n)
+    dense[ci[0], ci[1]] = cv
+    assert A.nnz() == ci.size(1)
+    assert torch.allclose(A.to_dense().cpu(), dense, rtol=1e-5, atol=1e-6)
+    assert torch.allclose((A @ x.to(cuda)).cpu(), dense @ x, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(matmul(A, x.to(cuda), "mean").cpu(),
+                          (dense @ x) / (dense != 0).sum(1).clamp(min=1).view(-1, 1), rtol=1e-4, atol=1e-4)
+    At = A.t()
+    assert At.sparse_sizes() == (n, m) and At.t() is A
+    y = torch.randn(m, F, generator=g)
+    assert torch.allclose((At @ y.to(cuda)).cpu(), dense.t() @ y, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(A.sum(dim=1).cpu(), dense.sum(1), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(A.sum(dim=0).cpu(), dense.sum(0), rtol=1e-5, atol=1e-5)
+    rowptr, col, v = A.csr()
+    assert rowptr.numel() == m + 1 and int(rowptr[-1]) == A.nnz()
