@@ -430,6 +430,8 @@ def run_rmat(args):
         plan, gidx = agg.plan()
         if args.exchange == "needed":
             x_full = torch.empty(agg.n_needed, F, device=dev, dtype=dtype)
+        elif args.exchange == "push":
+            x_full = agg.exchange_push(x_local)  # the symmetric receive buffer
     else:
         plan = planmod.build_plan(dst, n_out)
         gidx = plan.sorted_ids(src)
@@ -495,7 +497,7 @@ def run_rmat(args):
                        "max_row_len": plan.max_len, "empty_rows_rank0": plan.n_empty,
                        "exchange": args.exchange if world > 1 else None,
                        "exchange_bytes_in_rank0": ((agg.n_needed - agg.recv_splits[rank]) * F * es
-                                                   if (world > 1 and args.exchange == "needed")
+                                                   if (world > 1 and args.exchange in ("needed", "push"))
                                                    else (world - 1) * (N // world) * F * es),
                        "local_kernel_ms_max_over_ranks": k_ms_max,
                        "l2": "inputs larger than L2; no flush needed",
@@ -536,7 +538,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="products",
                     choices=sorted(WORKLOADS) + ["rmat26", "rmat24", "rmat22", "rmat20"])
-    ap.add_argument("--exchange", default="needed", choices=["allgather", "needed"],
+    ap.add_argument("--exchange", default="needed", choices=["allgather", "needed", "push"],
                     help="rmat workloads at N>1: all-gather every feature row, or only the rows each "
                          "rank's edges read (all-to-all)")
     ap.add_argument("--row-weight", type=int, default=4,

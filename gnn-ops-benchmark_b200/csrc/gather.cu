@@ -68,6 +68,39 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Fused gather + NVLink delivery of the needed-rows exchange: this rank owns x; for every row a
+// peer asked for, read it once from local HBM and store it straight into that peer's receive
+// buffer through its mapped peer pointer (posted 16-byte stores over NVLink 5 / NVSwitch).  One
+// kernel replaces "gather into a send buffer, then all-to-all": no staging copy, and the transfer
+// overlaps the gather row by row.  seg[q]..seg[q+1] are the slots requested by rank q; its rows
+// land at peer_buf[q] + (row_off[q] + slot - seg[q]) * dst_stride.
+constexpr int kMaxPeers = 16;
+struct PushParams {
+  const char* x;
+  const int64_t* serve_rows;
+  char* peer_buf[kMaxPeers];
+  int64_t seg[kMaxPeers + 1];
+  int64_t row_off[kMaxPeers];
+  int64_t row_bytes, src_stride, dst_stride, n_serve;
+  int P;
+};
+
+template <typename V>
+__global__ void __launch_bounds__(256) push_rows_kernel(const PushParams p) {
+  const int64_t vpr = p.row_bytes / (int64_t)sizeof(V);
+  const int64_t total = p.n_serve * vpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / vpr, j = i - s * vpr;
+    int q = 0;
+#pragma unroll 1
+    while (q + 1 < p.P && s >= p.seg[q + 1]) ++q;
+    const int64_t r = p.serve_rows[s];
+    const V v = __ldg(reinterpret_cast<const V*>(p.x + r * p.src_stride) + j);
+    reinterpret_cast<V*>(p.peer_buf[q] + (p.row_off[q] + (s - p.seg[q])) * p.dst_stride)[j] = v;
+  }
+}
+
 template <typename T, int RED>
 static int launch_lastdim(const gno_csr* g, const void* x, int64_t B, int64_t L, int64_t ldx,
                           void* out, int64_t ldo, int64_t* arg, int64_t arg_fill, int mean,
@@ -148,6 +181,50 @@ int gno_pad_rows(const void* src, int64_t rows, int64_t row_bytes, int64_t src_s
   GNO_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_stride_bytes, src, (size_t)src_stride_bytes,
                              (size_t)row_bytes, (size_t)rows, cudaMemcpyDeviceToDevice,
                              (cudaStream_t)stream));
+  return GNO_OK;
+}
+
+int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes, const int64_t* serve_rows,
+                  int64_t n_serve, int n_peers, void* const* peer_bufs, const int64_t* seg,
+                  const int64_t* row_off, int64_t dst_stride_bytes, gno_stream_t stream) {
+  if (n_serve == 0 || row_bytes == 0) return GNO_OK;
+  GNO_CHECK_ARG(x && serve_rows && peer_bufs && seg && row_off && n_serve > 0 && row_bytes > 0,
+                "gno_push_rows: bad argument");
+  GNO_CHECK_ARG(n_peers >= 1 && n_peers <= kMaxPeers, "gno_push_rows: 1..%d peers supported", kMaxPeers);
+  GNO_CHECK_ARG(src_stride_bytes >= row_bytes && dst_stride_bytes >= row_bytes, "gno_push_rows: bad stride");
+  PushParams p;
+  p.x = static_cast<const char*>(x);
+  p.serve_rows = serve_rows;
+  p.row_bytes = row_bytes;
+  p.src_stride = src_stride_bytes;
+  p.dst_stride = dst_stride_bytes;
+  p.n_serve = n_serve;
+  p.P = n_peers;
+  uintptr_t a = (uintptr_t)x | (uintptr_t)row_bytes | (uintptr_t)src_stride_bytes | (uintptr_t)dst_stride_bytes;
+  for (int q = 0; q < n_peers; ++q) {
+    p.peer_buf[q] = static_cast<char*>(peer_bufs[q]);
+    p.seg[q] = seg[q];
+    p.row_off[q] = row_off[q];
+    a |= (uintptr_t)peer_bufs[q];
+    GNO_CHECK_ARG(peer_bufs[q] != nullptr || seg[q + 1] == seg[q], "gno_push_rows: NULL peer buffer");
+  }
+  p.seg[n_peers] = seg[n_peers];
+  GNO_CHECK_ARG(seg[0] == 0 && seg[n_peers] == n_serve, "gno_push_rows: seg must cover [0, n_serve)");
+  cudaStream_t s = (cudaStream_t)stream;
+  auto grid = [](int64_t n) {
+    int64_t b = ceil_div(n, 256);
+    return (unsigned)(b > (int64_t)kNumSMs * 32 ? (int64_t)kNumSMs * 32 : b);
+  };
+  if (a % 16 == 0) {
+    push_rows_kernel<uint4><<<grid(n_serve * (row_bytes / 16)), 256, 0, s>>>(p);
+  } else if (a % 4 == 0) {
+    push_rows_kernel<uint32_t><<<grid(n_serve * (row_bytes / 4)), 256, 0, s>>>(p);
+  } else if (a % 2 == 0) {
+    push_rows_kernel<uint16_t><<<grid(n_serve * (row_bytes / 2)), 256, 0, s>>>(p);
+  } else {
+    push_rows_kernel<uint8_t><<<grid(n_serve * row_bytes), 256, 0, s>>>(p);
+  }
+  GNO_LAUNCHED("push_rows_kernel");
   return GNO_OK;
 }
 

@@ -94,10 +94,12 @@ class DistAggregator:
         self._gidx = None
         self._stage_plans = None
         self.exchange_mode = exchange
-        if exchange == "needed":
+        if exchange in ("needed", "push"):
             self._setup_needed(src_global, owner, local)
+            if exchange == "push":
+                self._setup_push()
         elif exchange != "allgather":
-            raise ValueError("exchange must be 'allgather' or 'needed'")
+            raise ValueError("exchange must be 'allgather', 'needed' or 'push'")
 
     # -- needed-rows-only exchange -------------------------------------------
     def _setup_needed(self, src_global, owner, local):
@@ -137,6 +139,61 @@ class DistAggregator:
             out = torch.empty((self.n_needed, x_local.size(1)), dtype=x_local.dtype, device=x_local.device)
         dist.all_to_all_single(out, send, self.recv_splits, self.send_splits, group=self.group)
         return out
+
+    # -- needed rows pushed over NVLink by the gather kernel itself -----------------------------
+    def _setup_push(self):
+        """exchange="push": the owners' gather kernel stores each requested row straight into the
+        requester's receive buffer through NVLink peer pointers (torch symmetric memory), instead
+        of gathering into a send buffer and calling an all-to-all.  Every owner needs to know where
+        its rows start inside each requester's buffer."""
+        dev = self.serve_rows.device
+        recv_off = torch.zeros(self.world, dtype=torch.int64)
+        recv_off[1:] = torch.cumsum(torch.tensor(self.recv_splits[:-1], dtype=torch.int64), 0)
+        recv_off = recv_off.to(dev)
+        row_off = torch.empty_like(recv_off)
+        n_max = torch.tensor([self.n_needed], dtype=torch.int64, device=dev)
+        if self.world > 1:
+            dist.all_to_all_single(row_off, recv_off, group=self.group)
+            dist.all_reduce(n_max, op=dist.ReduceOp.MAX, group=self.group)
+        else:
+            row_off.copy_(recv_off)
+        self._push_row_off = [int(v) for v in row_off.tolist()]
+        self._push_seg = [0]
+        for c in self.send_splits:
+            self._push_seg.append(self._push_seg[-1] + c)
+        self._push_rows_max = max(int(n_max.item()), 1)
+        self._push_bufs = {}
+
+    def _push_buffer(self, F, dtype, device):
+        key = (F, dtype)
+        st = self._push_bufs.get(key)
+        if st is None:
+            import ctypes
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty((self._push_rows_max, F), dtype=dtype, device=device)
+            hdl = symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            ptrs = (ctypes.c_void_p * self.world)(*[int(hdl.buffer_ptrs[q]) for q in range(self.world)])
+            seg = (ctypes.c_int64 * (self.world + 1))(*self._push_seg)
+            off = (ctypes.c_int64 * self.world)(*self._push_row_off)
+            st = self._push_bufs[key] = (t, hdl, ptrs, seg, off)
+        return st
+
+    def exchange_push(self, x_local):
+        import ctypes
+        from ._lib import check, lib
+        from .plan import _ptr, _stream
+        if x_local.size(0) != self.n_local:
+            raise ValueError("x_local must hold this rank's rows")
+        x_local = x_local.contiguous()
+        F, es = x_local.size(1), x_local.element_size()
+        t, hdl, ptrs, seg, off = self._push_buffer(F, x_local.dtype, x_local.device)
+        hdl.barrier(channel=0)  # every peer is done reading its buffer from the previous call
+        with torch.cuda.device(x_local.device):
+            check(lib.gno_push_rows(_ptr(x_local), F * es, x_local.stride(0) * es, _ptr(self.serve_rows),
+                                    self.serve_rows.numel(), self.world, ptrs, seg, off, F * es,
+                                    _stream(x_local.device)))
+        hdl.barrier(channel=1)  # every row has landed everywhere
+        return t[:self.n_needed]
 
     # -- exchange -------------------------------------------------------------------------------
     def _padded(self, x_local):
@@ -182,7 +239,7 @@ class DistAggregator:
         if self._plan is None:
             from . import plan as planmod
             self._plan = planmod.build_plan(self.dst_local, self.n_out)
-            ids = self.src_needed if self.exchange_mode == "needed" else self.src_padded
+            ids = self.src_needed if self.exchange_mode in ("needed", "push") else self.src_padded
             self._gidx = self._plan.sorted_ids(ids)
         return self._plan, self._gidx
 
@@ -214,7 +271,9 @@ class DistAggregator:
                 out.div_(cnt.view(-1, 1))
             return out
         plan, gidx = self.plan()
-        if self.exchange_mode == "needed":
+        if self.exchange_mode == "push":
+            xf = self.exchange_push(x_local)
+        elif self.exchange_mode == "needed":
             xf = self.exchange_needed(x_local, x_full)
         else:
             xf = self.exchange(x_local, x_full)

@@ -56,6 +56,12 @@ def _worker(rank, world, port, ret):
         got = aggn.aggregate(x[int(xb[rank]):int(xb[rank + 1])].to(dev), "max", return_arg=True)
         want, _ = oracle.gather_scatter(x, src, dst, N, "max")
         ok &= torch.equal(got[0].cpu(), want[lo:hi])
+        # the same exchange done by the fused gather + NVLink peer-store kernel (symmetric memory)
+        aggp = DistAggregator(bounds, shards[rank][0].to(dev), shards[rank][1].to(dev), feature_bounds=xb,
+                              exchange="push")
+        for _ in range(3):  # repeated calls reuse the receive buffer: exercises both barriers
+            got = aggp.aggregate(x[int(xb[rank]):int(xb[rank + 1])].to(dev), "max", return_arg=True)
+            ok &= torch.equal(got[0].cpu(), want[lo:hi])
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
