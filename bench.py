@@ -425,8 +425,19 @@ def run_rmat(args):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     if world > 1:
-        agg = DistAggregator(bounds, src, dst, rank=rank, world=world, feature_bounds=xb,
-                             exchange=args.exchange)
+        cyc = N if (args.cyclic and args.exchange != "allgather") else None
+        try:
+            agg = DistAggregator(bounds, src, dst, rank=rank, world=world, feature_bounds=xb,
+                                 exchange=args.exchange, cyclic_rows=cyc)
+            if args.exchange == "push":
+                agg.exchange_push(x_local)  # symmetric-memory rendezvous happens here
+        except Exception as ex:  # no peer mapping on this box: same exchange through NCCL all-to-all
+            if args.exchange != "push":
+                raise
+            print(f"push exchange unavailable ({ex!r}); using the NCCL needed-rows all-to-all", file=sys.stderr)
+            args.exchange = "needed"
+            agg = DistAggregator(bounds, src, dst, rank=rank, world=world, feature_bounds=xb,
+                                 exchange="needed", cyclic_rows=cyc)
         plan, gidx = agg.plan()
         if args.exchange == "needed":
             x_full = torch.empty(agg.n_needed, F, device=dev, dtype=dtype)
@@ -502,7 +513,9 @@ def run_rmat(args):
                        "local_kernel_ms_max_over_ranks": k_ms_max,
                        "l2": "inputs larger than L2; no flush needed",
                        "parallelism": f"edge-balanced dst ranges x{world}, equal feature blocks, "
-                                      "NCCL all-gather of x" if world > 1 else "single GPU"},
+                                      f"{args.exchange} exchange of x"
+                                      + (", cyclic feature ownership" if args.cyclic and args.exchange != "allgather" else "")
+                                      if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": None, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -538,9 +551,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="products",
                     choices=sorted(WORKLOADS) + ["rmat26", "rmat24", "rmat22", "rmat20"])
-    ap.add_argument("--exchange", default="needed", choices=["allgather", "needed", "push"],
-                    help="rmat workloads at N>1: all-gather every feature row, or only the rows each "
-                         "rank's edges read (all-to-all)")
+    ap.add_argument("--exchange", default="push", choices=["allgather", "needed", "push"],
+                    help="rmat workloads at N>1: all-gather every feature row; only the rows each rank's "
+                         "edges read through an NCCL all-to-all (needed); or the same rows stored directly "
+                         "into the peers' buffers by the gather kernel over NVLink (push)")
+    ap.add_argument("--cyclic", type=int, default=1,
+                    help="rmat workloads: feature row i lives on rank i %% N (balances the serving side "
+                         "of the needed-rows exchange); 0 = contiguous equal blocks")
     ap.add_argument("--row-weight", type=int, default=4,
                     help="rmat workloads: cost of one destination row in edge units when balancing ranges")
     ap.add_argument("--stages", type=int, default=0,

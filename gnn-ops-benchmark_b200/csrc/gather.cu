@@ -82,6 +82,8 @@ struct PushParams {
   int64_t seg[kMaxPeers + 1];
   int64_t row_off[kMaxPeers];
   int64_t row_bytes, src_stride, dst_stride, n_serve;
+  int64_t start;  // first slot this rank serves: rotating it per rank avoids all ranks pushing to
+                  // the same receiver at the same time (NVLink ingress incast)
   int P;
 };
 
@@ -91,7 +93,9 @@ __global__ void __launch_bounds__(256) push_rows_kernel(const PushParams p) {
   const int64_t total = p.n_serve * vpr;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t s = i / vpr, j = i - s * vpr;
+    const int64_t s0 = i / vpr, j = i - s0 * vpr;
+    int64_t s = s0 + p.start;
+    if (s >= p.n_serve) s -= p.n_serve;
     int q = 0;
 #pragma unroll 1
     while (q + 1 < p.P && s >= p.seg[q + 1]) ++q;
@@ -186,7 +190,8 @@ int gno_pad_rows(const void* src, int64_t rows, int64_t row_bytes, int64_t src_s
 
 int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes, const int64_t* serve_rows,
                   int64_t n_serve, int n_peers, void* const* peer_bufs, const int64_t* seg,
-                  const int64_t* row_off, int64_t dst_stride_bytes, gno_stream_t stream) {
+                  const int64_t* row_off, int64_t dst_stride_bytes, int64_t start_slot,
+                  gno_stream_t stream) {
   if (n_serve == 0 || row_bytes == 0) return GNO_OK;
   GNO_CHECK_ARG(x && serve_rows && peer_bufs && seg && row_off && n_serve > 0 && row_bytes > 0,
                 "gno_push_rows: bad argument");
@@ -199,6 +204,7 @@ int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes, co
   p.src_stride = src_stride_bytes;
   p.dst_stride = dst_stride_bytes;
   p.n_serve = n_serve;
+  p.start = (start_slot >= 0 && start_slot < n_serve) ? start_slot : 0;
   p.P = n_peers;
   uintptr_t a = (uintptr_t)x | (uintptr_t)row_bytes | (uintptr_t)src_stride_bytes | (uintptr_t)dst_stride_bytes;
   for (int q = 0; q < n_peers; ++q) {

@@ -59,7 +59,7 @@ class DistAggregator:
     """
 
     def __init__(self, bounds, src_global, dst_local, rank=None, world=None, group=None, stages=1,
-                 feature_bounds=None, exchange="allgather"):
+                 feature_bounds=None, exchange="allgather", cyclic_rows=None):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -69,15 +69,25 @@ class DistAggregator:
         # destination ranges of a skewed graph have very unequal row counts, and padding every
         # feature shard to the largest would inflate the all-gather; equal feature blocks do not.
         self.xbounds = self.bounds if feature_bounds is None else feature_bounds.to(torch.int64).cpu()
-        rows = self.xbounds[1:] - self.xbounds[:-1]
-        self.n_local = int(rows[self.rank])
-        self.max_rows = int(rows.max())
         self.dst_local = dst_local
+        if cyclic_rows is not None:
+            # Cyclic ownership (row i lives on rank i % P as local row i // P): spreads the hub rows
+            # of a skewed graph over all owners, so the needed-rows exchange is balanced on the
+            # SENDING side too (with contiguous blocks the owner of the low ids serves every rank).
+            n_rows = int(cyclic_rows)
+            self.n_local = (n_rows - self.rank + self.world - 1) // self.world
+            self.max_rows = (n_rows + self.world - 1) // self.world
+            owner = src_global % self.world
+            local = torch.div(src_global, self.world, rounding_mode="floor")
+        else:
+            rows = self.xbounds[1:] - self.xbounds[:-1]
+            self.n_local = int(rows[self.rank])
+            self.max_rows = int(rows.max())
+            # global source id -> (owner rank, row inside the owner's shard)
+            b = self.xbounds.to(src_global.device)
+            owner = torch.searchsorted(b[1:].contiguous(), src_global, right=True)
+            local = src_global - b[owner]
         self.stages = max(1, min(int(stages), max(self.max_rows, 1)))
-        # global source id -> (owner rank, row inside the owner's shard)
-        b = self.xbounds.to(src_global.device)
-        owner = torch.searchsorted(b[1:].contiguous(), src_global, right=True)
-        local = src_global - b[owner]
         # single-stage layout: row of the padded gather buffer [P * max_rows, F]
         self.src_padded = owner * self.max_rows + local
         # K-stage layout: chunk c holds rows [c*mc, c*mc + rows_c) of every shard
@@ -107,11 +117,11 @@ class DistAggregator:
         P=4: 26 %).  Each rank asks every owner for exactly the rows its edges read; per call the
         owners gather those rows and one all-to-all delivers them, already in the order of the
         sorted distinct source ids, so the gather index is just the rank of the id."""
-        uniq, inv = torch.unique(src_global, return_inverse=True)  # ascending => grouped by owner
-        b = self.xbounds.to(src_global.device)
-        uowner = torch.searchsorted(b[1:].contiguous(), uniq, right=True)
+        key = owner * self.max_rows + local                      # ascending key = grouped by owner
+        uniq, inv = torch.unique(key, return_inverse=True)
+        uowner = torch.div(uniq, self.max_rows, rounding_mode="floor")
         recv_counts = torch.bincount(uowner, minlength=self.world)
-        req = uniq - b[uowner]
+        req = uniq - uowner * self.max_rows                        # row inside the owner's shard
         if self.world > 1:
             send_counts = torch.empty_like(recv_counts)
             dist.all_to_all_single(send_counts, recv_counts, group=self.group)
@@ -191,6 +201,7 @@ class DistAggregator:
         with torch.cuda.device(x_local.device):
             check(lib.gno_push_rows(_ptr(x_local), F * es, x_local.stride(0) * es, _ptr(self.serve_rows),
                                     self.serve_rows.numel(), self.world, ptrs, seg, off, F * es,
+                                    self._push_seg[(self.rank + 1) % self.world],
                                     _stream(x_local.device)))
         hdl.barrier(channel=1)  # every row has landed everywhere
         return t[:self.n_needed]

@@ -221,7 +221,9 @@ int gno_gather_rows(const void* x, int64_t x_rows, int64_t row_bytes,
  * n_peers+1 / n_peers entries), read x[serve_rows[slot]] once from local HBM
  * and store it directly into that peer's receive buffer through its mapped
  * peer pointer (peer_bufs[q], e.g. from torch symmetric memory / CUDA IPC) at
- * row row_off[q] + slot - seg[q].  Replaces "gather into a send buffer, then
+ * row row_off[q] + slot - seg[q].  Slots are served in rotated order starting
+ * at start_slot (pass seg[(rank+1) % n_peers]) so that at any moment the ranks
+ * push to different receivers.  Replaces "gather into a send buffer, then
  * all-to-all"; the caller provides the cross-rank barrier (new work, no
  * reference counterpart: the reference is single-GPU).
  */
@@ -229,7 +231,7 @@ int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes,
                   const int64_t* serve_rows, int64_t n_serve, int n_peers,
                   void* const* peer_bufs, const int64_t* seg,
                   const int64_t* row_off, int64_t dst_stride_bytes,
-                  gno_stream_t stream);
+                  int64_t start_slot, gno_stream_t stream);
 
 /* -------------------------------------------- element-wise index form -- */
 /*

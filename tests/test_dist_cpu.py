@@ -67,6 +67,11 @@ def _worker(rank, world, port, N, E, F, ret):
         ok &= recv.size(0) == torch.unique(s_r).numel()
         got, _ = oracle.gather_scatter(recv, aggn.src_needed, d_r, hi - lo, "sum")
         ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
+        # cyclic feature ownership (row i on rank i % P): balanced serving of hub rows
+        aggc = DistAggregator(bounds, s_r, d_r, exchange="needed", cyclic_rows=N)
+        recv = aggc.exchange_needed(x[rank::world].contiguous())
+        got, _ = oracle.gather_scatter(recv, aggc.src_needed, d_r, hi - lo, "sum")
+        ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
         ret[rank] = (bool(ok), int(d_r.numel()))
     finally:
         dist.destroy_process_group()
