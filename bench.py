@@ -203,7 +203,20 @@ def run_ours(args):
     if world > 1:
         from gno_b200.dist import DistAggregator
         bounds = torch.arange(world + 1, dtype=torch.int64) * n_local
-        agg = DistAggregator(bounds, src, dst, rank=rank, world=world, stages=args.stages)
+        # measured (profiles/scaling): the peer-store all-gather beats NCCL at N=2 (6.64 vs 7.18 ms),
+        # ties at N=4 (10.16 vs 10.04) and loses at N=8 (17.4 vs 15.6)
+        xmode = args.exchange if args.exchange in ("allgather", "allgather_push") else \
+            ("allgather_push" if world <= 2 else "allgather")
+        try:
+            agg = DistAggregator(bounds, src, dst, rank=rank, world=world, stages=args.stages, exchange=xmode)
+            if xmode == "allgather_push":
+                x_full = agg.exchange_allgather_push(x_local)  # symmetric-memory rendezvous happens here
+        except Exception as ex:  # no peer mapping on this box: NCCL all-gather
+            if xmode != "allgather_push":
+                raise
+            print(f"allgather_push unavailable ({ex!r}); using the NCCL all-gather", file=sys.stderr)
+            xmode = "allgather"
+            agg = DistAggregator(bounds, src, dst, rank=rank, world=world, stages=args.stages)
         plan, gidx = agg.plan()
         if args.stages > 1:
             agg.stage_plans()
@@ -353,8 +366,9 @@ def run_ours(args):
                        "plan_build_ms": plan_ms, "max_row_len": plan.max_len,
                        "chunk_len": plan.chunk_len, "rows_cut_by_chunks": plan.n_span,
                        "empty_rows": plan.n_empty,
-                       "parallelism": (f"dst-partitioned x{world}, NCCL all-gather of x, {args.stages}-stage "
-                                       "pipelined exchange") if world > 1 else "single GPU"},
+                       "parallelism": (f"dst-partitioned x{world}, all-gather of x by "
+                                       + ("peer-store kernel over NVLink (gno_push_rows)" if xmode == "allgather_push"
+                                          else f"NCCL, {args.stages}-stage exchange")) if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -551,7 +565,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="products",
                     choices=sorted(WORKLOADS) + ["rmat26", "rmat24", "rmat22", "rmat20"])
-    ap.add_argument("--exchange", default="push", choices=["allgather", "needed", "push"],
+    ap.add_argument("--exchange", default="push", choices=["allgather", "allgather_push", "needed", "push"],
                     help="rmat workloads at N>1: all-gather every feature row; only the rows each rank's "
                          "edges read through an NCCL all-to-all (needed); or the same rows stored directly "
                          "into the peers' buffers by the gather kernel over NVLink (push)")

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) push_rows_kernel(const PushParams p) {
     int q = 0;
 #pragma unroll 1
     while (q + 1 < p.P && s >= p.seg[q + 1]) ++q;
-    const int64_t r = p.serve_rows[s];
+    const int64_t r = p.serve_rows ? p.serve_rows[s] : (s - p.seg[q]);  // NULL: every peer gets all rows
     const V v = __ldg(reinterpret_cast<const V*>(p.x + r * p.src_stride) + j);
     reinterpret_cast<V*>(p.peer_buf[q] + (p.row_off[q] + (s - p.seg[q])) * p.dst_stride)[j] = v;
   }
@@ -193,7 +193,7 @@ int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes, co
                   const int64_t* row_off, int64_t dst_stride_bytes, int64_t start_slot,
                   gno_stream_t stream) {
   if (n_serve == 0 || row_bytes == 0) return GNO_OK;
-  GNO_CHECK_ARG(x && serve_rows && peer_bufs && seg && row_off && n_serve > 0 && row_bytes > 0,
+  GNO_CHECK_ARG(x && peer_bufs && seg && row_off && n_serve > 0 && row_bytes > 0,
                 "gno_push_rows: bad argument");
   GNO_CHECK_ARG(n_peers >= 1 && n_peers <= kMaxPeers, "gno_push_rows: 1..%d peers supported", kMaxPeers);
   GNO_CHECK_ARG(src_stride_bytes >= row_bytes && dst_stride_bytes >= row_bytes, "gno_push_rows: bad stride");

@@ -221,7 +221,8 @@ int gno_gather_rows(const void* x, int64_t x_rows, int64_t row_bytes,
  * n_peers+1 / n_peers entries), read x[serve_rows[slot]] once from local HBM
  * and store it directly into that peer's receive buffer through its mapped
  * peer pointer (peer_bufs[q], e.g. from torch symmetric memory / CUDA IPC) at
- * row row_off[q] + slot - seg[q].  Slots are served in rotated order starting
+ * row row_off[q] + slot - seg[q].  serve_rows == NULL sends row slot - seg[q]
+ * (every peer receives all local rows: an all-gather by peer stores).  Slots are served in rotated order starting
  * at start_slot (pass seg[(rank+1) % n_peers]) so that at any moment the ranks
  * push to different receivers.  Replaces "gather into a send buffer, then
  * all-to-all"; the caller provides the cross-rank barrier (new work, no

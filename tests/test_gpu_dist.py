@@ -62,6 +62,10 @@ def _worker(rank, world, port, ret):
         for _ in range(3):  # repeated calls reuse the receive buffer: exercises both barriers
             got = aggp.aggregate(x[int(xb[rank]):int(xb[rank + 1])].to(dev), "max", return_arg=True)
             ok &= torch.equal(got[0].cpu(), want[lo:hi])
+        agga = DistAggregator(bounds, shards[rank][0].to(dev), shards[rank][1].to(dev), exchange="allgather_push")
+        for _ in range(2):
+            got = agga.aggregate(x[lo:hi].to(dev), "max", return_arg=True)
+            ok &= torch.equal(got[0].cpu(), want[lo:hi])
         aggc = DistAggregator(bounds, shards[rank][0].to(dev), shards[rank][1].to(dev), exchange="push",
                               cyclic_rows=N)
         got = aggc.aggregate(x[rank::world].contiguous().to(dev), "max", return_arg=True)
