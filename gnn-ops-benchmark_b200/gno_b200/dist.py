@@ -138,13 +138,17 @@ class DistAggregator:
         self.n_needed = int(uniq.numel())
         self.src_needed = inv            # per-edge row of the received buffer
 
-    def exchange_needed(self, x_local, out=None):
-        """Gather the rows other ranks asked for and deliver them with one all-to-all."""
-        from . import ops
+    def exchange_needed(self, x_local, out=None, gather_rows=None):
+        """Gather the rows other ranks asked for and deliver them with one all-to-all.
+        gather_rows(x, rows) defaults to the CUDA row-gather kernel (gno_gather_rows); the gloo
+        host-logic tests inject their own, the product has no CPU path."""
         if x_local.size(0) != self.n_local:
             raise ValueError("x_local must hold this rank's rows")
-        send = ops.index_select(x_local, 0, self.serve_rows) if x_local.is_cuda else \
-            x_local.index_select(0, self.serve_rows)
+        if gather_rows is None:
+            from . import ops
+            send = ops.index_select(x_local, 0, self.serve_rows)
+        else:
+            send = gather_rows(x_local, self.serve_rows)
         if self.world == 1:
             return send
         if out is None:

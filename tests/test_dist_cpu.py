@@ -63,13 +63,13 @@ def _worker(rank, world, port, N, E, F, ret):
         xb = torch.tensor([0, 100, N])
         aggn = DistAggregator(bounds, s_r, d_r, feature_bounds=xb, exchange="needed")
         xlo, xhi = int(xb[rank]), int(xb[rank + 1])
-        recv = aggn.exchange_needed(x[xlo:xhi].contiguous())
+        recv = aggn.exchange_needed(x[xlo:xhi].contiguous(), gather_rows=lambda t, r: t.index_select(0, r))
         ok &= recv.size(0) == torch.unique(s_r).numel()
         got, _ = oracle.gather_scatter(recv, aggn.src_needed, d_r, hi - lo, "sum")
         ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
         # cyclic feature ownership (row i on rank i % P): balanced serving of hub rows
         aggc = DistAggregator(bounds, s_r, d_r, exchange="needed", cyclic_rows=N)
-        recv = aggc.exchange_needed(x[rank::world].contiguous())
+        recv = aggc.exchange_needed(x[rank::world].contiguous(), gather_rows=lambda t, r: t.index_select(0, r))
         got, _ = oracle.gather_scatter(recv, aggc.src_needed, d_r, hi - lo, "sum")
         ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
         ret[rank] = (bool(ok), int(d_r.numel()))
