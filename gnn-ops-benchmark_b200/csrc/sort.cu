@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 4 : 3)
     radix_scatter_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                          const ValT* __restrict__ vals_in, ValT* __restrict__ vals_out,
                          const int32_t* __restrict__ offsets, int64_t n, int shift, unsigned mask,
-                         int subtiles, int64_t num_tiles) {
+                         int nbits, int subtiles, int64_t num_tiles) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScatterSmem<KeyT, ValT, HAS_VAL>& sm = *reinterpret_cast<ScatterSmem<KeyT, ValT, HAS_VAL>*>(smem_raw);
 
@@ -89,12 +89,15 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 4 : 3)
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
       const unsigned d = (unsigned)(key[i] >> shift) & mask;
-      // lanes holding the same digit: 8 ballots (MATCH.ANY measured ~3x slower on sm_100a)
+      // lanes holding the same digit: one ballot per digit bit (MATCH.ANY measured slower on
+      // sm_100a); passes are split evenly, so most digits are narrower than 8 bits
       unsigned peers = 0xffffffffu;
 #pragma unroll
       for (int b = 0; b < 8; ++b) {
-        const unsigned vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
-        peers &= ((d >> b) & 1u) ? vote : ~vote;
+        if (b < nbits) {
+          const unsigned vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+          peers &= ((d >> b) & 1u) ? vote : ~vote;
+        }
       }
       const int leader = __ffs(peers) - 1;
       int old = 0;
@@ -228,12 +231,15 @@ static int sort_impl(const KeyT* keys_in, KeyT* keys_out, const ValT* vals_in, V
   }
   const KeyT* src_k = keys_in;
   const ValT* src_v = vals_in;
+  // split the bit range evenly over the passes (18 bits -> 6+6+6 rather than 8+8+2): the ranking
+  // costs one ballot per digit bit
+  const int total_bits = end_bit - begin_bit;
+  int shift = begin_bit;
   for (int p = 0; p < passes; ++p) {
     const bool to_out = ((passes - 1 - p) % 2) == 0;
     KeyT* dst_k = to_out ? keys_out : keys_alt;
     ValT* dst_v = to_out ? vals_out : vals_alt;
-    const int shift = begin_bit + 8 * p;
-    const int nb = min(8, end_bit - shift);
+    const int nb = total_bits / passes + (p < total_bits % passes ? 1 : 0);
     const unsigned mask = (1u << nb) - 1u;
     radix_hist_kernel<KeyT><<<(unsigned)g.num_tiles, kSortThreads, 0, s>>>(
         src_k, counts, n, shift, mask, g.tile_keys, g.num_tiles);
@@ -241,10 +247,11 @@ static int sort_impl(const KeyT* keys_in, KeyT* keys_out, const ValT* vals_in, V
     int rc = exclusive_scan_i32(counts, counts, (int64_t)kRadix * g.num_tiles, scan_ws, s);
     if (rc) return rc;
     radix_scatter_kernel<KeyT, ValT, HAS_VAL><<<(unsigned)g.num_tiles, kSortThreads, smem_bytes, s>>>(
-        src_k, dst_k, src_v, dst_v, counts, n, shift, mask, g.subtiles, g.num_tiles);
+        src_k, dst_k, src_v, dst_v, counts, n, shift, mask, nb, g.subtiles, g.num_tiles);
     GNO_LAUNCHED("radix_scatter_kernel");
     src_k = dst_k;
     src_v = dst_v;
+    shift += nb;
   }
   return GNO_OK;
 }
