@@ -105,6 +105,38 @@ __global__ void __launch_bounds__(256) push_rows_kernel(const PushParams p) {
   }
 }
 
+
+// Batched 2-D transpose out[o, c, r] = in[o, r, c] through a padded 32x32 shared-memory tile
+// (coalesced on both sides).  Moves the sorted dim of an inner-dim torch.sort last and back.
+template <typename V>
+__global__ void __launch_bounds__(256)
+    transpose_tiles_kernel(const V* __restrict__ in, V* __restrict__ out, int64_t rows, int64_t cols,
+                           int64_t tiles_r, int64_t tiles_c, int64_t n_tiles) {
+  __shared__ V tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t o = t / (tiles_r * tiles_c);
+    const int64_t rem = t - o * tiles_r * tiles_c;
+    const int64_t tr = rem / tiles_c, tc = rem - tr * tiles_c;
+    const V* src = in + o * rows * cols;
+    V* dst = out + o * rows * cols;
+    const int64_t c = tc * 32 + tx;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const int64_t r = tr * 32 + ty + j;
+      if (r < rows && c < cols) tile[ty + j][tx] = src[r * cols + c];
+    }
+    __syncthreads();
+    const int64_t r2 = tr * 32 + tx;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const int64_t c2 = tc * 32 + ty + j;
+      if (r2 < rows && c2 < cols) dst[c2 * rows + r2] = tile[tx][ty + j];
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T, int RED>
 static int launch_lastdim(const gno_csr* g, const void* x, int64_t B, int64_t L, int64_t ldx,
                           void* out, int64_t ldo, int64_t* arg, int64_t arg_fill, int mean,
@@ -231,6 +263,27 @@ int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes, co
     push_rows_kernel<uint8_t><<<grid(n_serve * row_bytes), 256, 0, s>>>(p);
   }
   GNO_LAUNCHED("push_rows_kernel");
+  return GNO_OK;
+}
+
+int gno_transpose_batched(const void* in, void* out, int64_t outer, int64_t rows, int64_t cols,
+                          int elem_bytes, gno_stream_t stream) {
+  GNO_CHECK_ARG(outer >= 0 && rows >= 0 && cols >= 0, "gno_transpose_batched: negative size");
+  GNO_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "gno_transpose_batched: elem_bytes must be 4 or 8");
+  if (outer == 0 || rows == 0 || cols == 0) return GNO_OK;
+  GNO_CHECK_ARG(in && out && in != out, "gno_transpose_batched: NULL or aliased buffer");
+  GNO_CHECK_ARG((((uintptr_t)in | (uintptr_t)out) % elem_bytes) == 0, "gno_transpose_batched: misaligned buffer");
+  const int64_t tiles_r = ceil_div(rows, 32), tiles_c = ceil_div(cols, 32);
+  const int64_t n_tiles = outer * tiles_r * tiles_c;
+  const unsigned grid = (unsigned)imin64(n_tiles, (int64_t)kNumSMs * 64);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (elem_bytes == 4)
+    transpose_tiles_kernel<uint32_t><<<grid, 256, 0, s>>>((const uint32_t*)in, (uint32_t*)out, rows, cols,
+                                                           tiles_r, tiles_c, n_tiles);
+  else
+    transpose_tiles_kernel<uint64_t><<<grid, 256, 0, s>>>((const uint64_t*)in, (uint64_t*)out, rows, cols,
+                                                           tiles_r, tiles_c, n_tiles);
+  GNO_LAUNCHED("transpose_tiles_kernel");
   return GNO_OK;
 }
 

@@ -7,7 +7,7 @@ without the built CUDA library raises.
 """
 from . import _lib, autograd, dist, host, ops, plan  # noqa: F401
 from ._lib import GnoError, launch_count  # noqa: F401
-from .ops import (clear_caches, coalesce, gather_csr, gather_scatter, index_add,  # noqa: F401
-                  index_select, scatter, segment_csr, segment_reduce, sort, sort_pairs, spmm,
+from .ops import (clear_caches, coalesce, gather_coo, gather_csr, gather_scatter, index_add,  # noqa: F401
+                  index_select, scatter, segment_coo, segment_csr, segment_reduce, sort, sort_pairs, spmm,
                   spmm_csr, transpose)
 from .plan import CSRPlan, build_plan, plan_cache, plan_from_rowptr  # noqa: F401

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "gno_abi_version": (c_int, []),
     "gno_last_error": (c_char_p, []),
     "gno_launch_count": (c_int64, []),
+    "gno_transpose_batched": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "gno_sort_pairs_workspace": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),
     "gno_sort_pairs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                c_int, c_int, c_void_p, c_size_t, c_void_p]),
@@ -112,3 +113,4 @@ def check(rc):
 
 def launch_count():
     return int(lib.gno_launch_count())
+

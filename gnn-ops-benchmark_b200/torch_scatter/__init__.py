@@ -116,6 +116,40 @@ def gather_csr(src: torch.Tensor, indptr: torch.Tensor,
     return _ops.gather_csr(src, indptr)
 
 
+def segment_coo(src: torch.Tensor, index: torch.Tensor, out: Optional[torch.Tensor] = None,
+                dim_size: Optional[int] = None, reduce: str = "sum") -> torch.Tensor:
+    if reduce not in ("sum", "add", "mean", "min", "max"):
+        raise ValueError
+    return _ops.segment_coo(src, index, out, dim_size, reduce)
+
+
+def segment_sum_coo(src, index, out=None, dim_size=None):
+    return segment_coo(src, index, out, dim_size, "sum")
+
+
+def segment_add_coo(src, index, out=None, dim_size=None):
+    return segment_coo(src, index, out, dim_size, "sum")
+
+
+def segment_mean_coo(src, index, out=None, dim_size=None):
+    return segment_coo(src, index, out, dim_size, "mean")
+
+
+def segment_min_coo(src, index, out=None, dim_size=None):
+    return _ops.segment_coo(src, index, out, dim_size, "min", return_arg=True)
+
+
+def segment_max_coo(src, index, out=None, dim_size=None):
+    return _ops.segment_coo(src, index, out, dim_size, "max", return_arg=True)
+
+
+def gather_coo(src: torch.Tensor, index: torch.Tensor,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is not None:
+        raise NotImplementedError("gno_b200 gather_coo: out= is not supported")
+    return _ops.gather_coo(src, index)
+
+
 from .composite import (scatter_log_softmax, scatter_logsumexp, scatter_softmax,  # noqa: E402
                         scatter_std)
 
@@ -123,5 +157,6 @@ __all__ = [
     "scatter_std", "scatter_logsumexp", "scatter_softmax", "scatter_log_softmax",
     "scatter_sum", "scatter_add", "scatter_mul", "scatter_mean", "scatter_min", "scatter_max",
     "scatter", "segment_csr", "segment_sum_csr", "segment_add_csr", "segment_mean_csr",
-    "segment_min_csr", "segment_max_csr", "gather_csr",
+    "segment_min_csr", "segment_max_csr", "gather_csr", "segment_coo", "segment_sum_coo",
+    "segment_add_coo", "segment_mean_coo", "segment_min_coo", "segment_max_coo", "gather_coo",
 ]

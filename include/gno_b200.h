@@ -209,6 +209,14 @@ int gno_pad_rows(const void* src, int64_t rows, int64_t row_bytes,
                  int64_t src_stride_bytes, void* dst, int64_t dst_stride_bytes,
                  gno_stream_t stream);
 
+/* Batched 2-D transpose out[o, c, r] = in[o, r, c] of 4- or 8-byte elements
+ * (32x32 shared-memory tiles).  Used by gno_b200.sort to move an inner sorted
+ * dim last and back: torch.sort(input, dim=0) of
+ * op_bm_scripts/benchmark_native_sort.py:28-30. */
+int gno_transpose_batched(const void* in, void* out, int64_t outer,
+                          int64_t rows, int64_t cols, int elem_bytes,
+                          gno_stream_t stream);
+
 /* out[k, :] = x[index[k], :]  (row gather with 128-bit accesses): the
  * un-fused index_select of benchmark_native_index_select.py:12-15. */
 int gno_gather_rows(const void* x, int64_t x_rows, int64_t row_bytes,

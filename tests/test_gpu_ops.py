@@ -461,3 +461,59 @@ def test_sparse_tensor(cuda):
     assert torch.allclose(A.sum(dim=0).cpu(), dense.sum(0), rtol=1e-5, atol=1e-5)
     rowptr, col, v = A.csr()
     assert rowptr.numel() == m + 1 and int(rowptr[-1]) == A.nnz()
+
+
+# ---- segment_coo / gather_coo (torch_scatter's sorted-index forms, reached through PyG) ----------
+@pytest.mark.parametrize("reduce", ["sum", "mean", "min", "max"])
+@pytest.mark.parametrize("batched", [False, True])
+def test_segment_coo(cuda, reduce, batched):
+    import torch_scatter
+    g = torch.Generator().manual_seed(21)
+    E, K, N = 700, 6, 40
+    if batched:
+        src = (torch.randn(3, E, K, generator=g) * 4).round() / 4
+        index = torch.sort(torch.randint(0, N, (3, E), generator=g), dim=1).values
+        full = index.unsqueeze(-1).expand_as(src)
+        want, warg = oracle.scatter(src, full, 1, N, reduce)
+    else:
+        src = (torch.randn(E, K, generator=g) * 4).round() / 4
+        index = torch.sort(torch.randint(0, N, (E,), generator=g)).values
+        want, warg = oracle.scatter(src, index, 0, N, reduce)
+    got = torch_scatter.segment_coo(src.to(cuda), index.to(cuda), dim_size=N, reduce=reduce)
+    if reduce in ("min", "max"):
+        assert torch.equal(got.cpu(), want)
+        fn = torch_scatter.segment_max_coo if reduce == "max" else torch_scatter.segment_min_coo
+        v, a = fn(src.to(cuda), index.to(cuda), None, N)
+        assert torch.equal(v.cpu(), want) and torch.equal(a.cpu(), warg)
+    else:
+        close(got, want, torch.float32, None if reduce == "mean" else
+              oracle.scatter(src.abs(), full if batched else index, 1 if batched else 0, N, "sum")[0])
+    # dim_size=None: last segment id + 1 (one host sync, as upstream)
+    got2 = torch_scatter.segment_coo(src.to(cuda), index.to(cuda), reduce="sum")
+    assert got2.size(index.dim() - 1) == int(index.max()) + 1
+
+
+def test_gather_coo(cuda):
+    import torch_scatter
+    g = torch.Generator().manual_seed(22)
+    src = torch.randn(50, 7, generator=g)
+    index = torch.sort(torch.randint(0, 50, (300,), generator=g)).values
+    got = torch_scatter.gather_coo(src.to(cuda), index.to(cuda))
+    assert torch.equal(got.cpu(), src.index_select(0, index))
+    src3 = torch.randn(4, 50, 3, generator=g)
+    index2 = torch.sort(torch.randint(0, 50, (4, 120), generator=g), dim=1).values
+    got = torch_scatter.gather_coo(src3.to(cuda), index2.to(cuda))
+    want = src3.gather(1, index2.unsqueeze(-1).expand(4, 120, 3))
+    assert torch.equal(got.cpu(), want)
+    src1 = torch.randn(64, generator=g)
+    got = torch_scatter.gather_coo(src1.to(cuda), index[:100].clamp(max=63).to(cuda))
+    assert torch.equal(got.cpu(), src1[index[:100].clamp(max=63)])
+
+
+@pytest.mark.parametrize("outer,rows,cols", [(1, 33, 65), (3, 100, 7), (2, 1, 50), (1, 1000, 1000)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.int64])
+def test_transpose_batched(cuda, outer, rows, cols, dtype):
+    from gno_b200 import ops
+    x = torch.arange(outer * rows * cols).view(outer, rows, cols).to(dtype)
+    got = ops._transpose_batched(x.to(cuda), outer, rows, cols).view(outer, cols, rows)
+    assert torch.equal(got.cpu(), x.transpose(1, 2).contiguous())
