@@ -162,13 +162,21 @@ __device__ __forceinline__ bool better(float v, float cur) {
   return v < cur;
 }
 
+// IEEE division kept out of line: flush_row is inlined at every row-boundary site of the
+// unrolled loops, and an inline quotient (reciprocal, Newton step, slow-path call) per element
+// and per site grew the kernel by two thirds.
+__device__ __noinline__ float div_rn_call(float a, float b) { return __fdiv_rn(a, b); }
+
 // Final element transform shared by the direct and the combine path.
-// cnt > 0 selects the mean (divide the sum by the row length, clamped to 1).
+// mean: divide the sum by cnt, the row length clamped to 1.  cnt must be a normal number >= 1
+// even when mean is off: the compiler evaluates the quotient speculatively, and a zero divisor
+// sends every element through the division's slow-path subroutine (ncu source view of the RMAT
+// shard: 24 % of all executed instructions before this was fixed).
 template <typename T, int RED>
-__device__ __forceinline__ float finalize(float a, int e, float prev, float cnt, int accumulate,
-                                          int64_t arg_fill, int64_t* arg_out) {
+__device__ __forceinline__ float finalize(float a, int e, float prev, bool mean, float cnt,
+                                          int accumulate, int64_t arg_fill, int64_t* arg_out) {
   if constexpr (RED == GNO_SUM) {
-    if (cnt > 0.f) a = a / cnt;
+    if (mean) a = div_rn_call(a, cnt);
     if (accumulate) a += prev;
   } else if constexpr (RED == GNO_MUL) {
     if (accumulate) a *= prev;
@@ -199,7 +207,8 @@ __device__ __forceinline__ void flush_row(const SegParams& p, int row, int chunk
     }
     return;
   }
-  const float cnt = p.mean ? (float)(seg_len > 1 ? seg_len : 1) : 0.f;
+  const float cnt = (float)(seg_len > 1 ? seg_len : 1);
+  const bool mean = p.mean != 0;
   if (p.vec_out) {
     char* optr = static_cast<char*>(p.out) + (int64_t)row * p.ldo_bytes + (int64_t)v * VB;
     Words<VB> prev;
@@ -214,7 +223,7 @@ __device__ __forceinline__ void flush_row(const SegParams& p, int row, int chunk
         e = ae[i];
       }
       const float pf = p.accumulate ? elem<T, VB>(prev, i) : 0.f;
-      set_elem<T, VB>(o, i, finalize<T, RED>(acc[i], e, pf, cnt, p.accumulate, p.arg_fill, ap));
+      set_elem<T, VB>(o, i, finalize<T, RED>(acc[i], e, pf, mean, cnt, p.accumulate, p.arg_fill, ap));
     }
     st_vec<VB>(optr, o);
   } else {
@@ -232,7 +241,7 @@ __device__ __forceinline__ void flush_row(const SegParams& p, int row, int chunk
           e = ae[i];
         }
         const float pf = p.accumulate ? DType<T>::to_f(orow[col]) : 0.f;
-        orow[col] = DType<T>::from_f(finalize<T, RED>(acc[i], e, pf, cnt, p.accumulate, p.arg_fill, ap));
+        orow[col] = DType<T>::from_f(finalize<T, RED>(acc[i], e, pf, mean, cnt, p.accumulate, p.arg_fill, ap));
       }
     }
   }
@@ -595,6 +604,13 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
   }
 }
 
+// Empty rows can be filled with 16-byte stores: out rows 16-byte aligned and a multiple of 16
+// bytes long (which makes the int64 arg rows multiples of 16 bytes too).
+__host__ __device__ static inline bool seg_fill16(const SegParams& p, int es, bool arg) {
+  return ((uintptr_t)p.out % 16 == 0) && (p.ldo_bytes % 16 == 0) && ((p.F * es) % 16 == 0) &&
+         (!arg || !p.arg || (uintptr_t)p.arg % 16 == 0);
+}
+
 // Finish pass: (a) rows cut by a chunk boundary — combine their partials in
 // chunk order: the tail slot of the first chunk, then the head slot of every
 // later chunk; (b) empty rows — write zeros (and arg_fill).  One thread per
@@ -603,15 +619,45 @@ template <typename T, int RED, bool ARG>
 __global__ void __launch_bounds__(256) segfinish_kernel(const SegParams p) {
   const int64_t Q = (p.F + 3) / 4;  // feature quads per row
   const int64_t n_a = p.n_span * Q;
-  const int64_t total = n_a + (p.accumulate ? 0 : p.n_empty * Q);
+  // Empty rows are a pure fill: 16-byte stores when the rows allow it (RMAT-26 leaves tens of
+  // millions of rows without an edge — at 8 bytes per thread this pass was 14 % of the step).
+  constexpr int EPV16 = 16 / (int)sizeof(T);
+  const bool fill16 = seg_fill16(p, (int)sizeof(T), ARG);
+  const int64_t per_empty = fill16 ? p.F / EPV16 : Q;
+  const int64_t total = n_a + (p.accumulate ? 0 : p.n_empty * per_empty);
   const bool vec_val = ((uintptr_t)p.out % (4 * sizeof(T)) == 0) && (p.ldo_bytes % (4 * sizeof(T)) == 0);
   const bool vec_arg = ARG && p.arg && ((uintptr_t)p.arg % 16 == 0) && (p.F % 2 == 0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
+    if (i >= n_a && fill16) {
+      const int64_t j = i - n_a;
+      int64_t z, c;
+      if (total < (int64_t(1) << 31)) {  // 32-bit division when it fits
+        z = (unsigned)j / (unsigned)per_empty;
+        c = (unsigned)j - (unsigned)z * (unsigned)per_empty;
+      } else {
+        z = j / per_empty;
+        c = j - z * per_empty;
+      }
+      const int64_t row = p.zrow[z];
+      // the reduction's identity through finalize: 0 (sum/mean/min/max), 1 (mul)
+      const float fv = finalize<T, RED>(red_init<T, RED>(), kNoArg, 0.f, false, 1.f, 0, p.arg_fill, nullptr);
+      Words<16> o;
+#pragma unroll
+      for (int q = 0; q < EPV16; ++q) set_elem<T, 16>(o, q, fv);
+      st_vec<16>(static_cast<char*>(p.out) + row * p.ldo_bytes + c * 16, o);
+      if constexpr (ARG) {
+        if (p.arg) {
+          longlong2* ap = reinterpret_cast<longlong2*>(p.arg + row * p.F + c * EPV16);
+#pragma unroll
+          for (int q = 0; q < EPV16 / 2; ++q) ap[q] = make_longlong2(p.arg_fill, p.arg_fill);
+        }
+      }
+      continue;
+    }
     float a[4];
     int e[4];
     int64_t row, f0;
-    float cnt = 0.f;
     if (i < n_a) {
       const int64_t s = i / Q;
       f0 = (i - s * Q) * 4;
@@ -662,7 +708,7 @@ __global__ void __launch_bounds__(256) segfinish_kernel(const SegParams p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) a[j] = (float)ad[j];
       }
-      // (mean already applied above in fp64; cnt stays 0 so finalize does not divide again)
+      // (mean already applied above in fp64: finalize is called with mean = false)
     } else {
       const int64_t j = i - n_a;
       const int64_t z = j / Q;
@@ -686,7 +732,7 @@ __global__ void __launch_bounds__(256) segfinish_kernel(const SegParams p) {
       const bool in = (f0 + q < p.F);
       const float prev = (p.accumulate && in) ? DType<T>::to_f(orow[f0 + q]) : 0.f;
       int64_t av = 0;
-      r[q] = finalize<T, RED>(a[q], e[q], prev, cnt, p.accumulate, p.arg_fill, arow ? &av : nullptr);
+      r[q] = finalize<T, RED>(a[q], e[q], prev, false, 1.f, p.accumulate, p.arg_fill, arow ? &av : nullptr);
       ra[q] = av;
     }
     if (full && vec_val) {
@@ -737,7 +783,8 @@ static int launch_seg(const SegParams& p, cudaStream_t s) {
     GNO_LAUNCHED("segreduce_kernel");
   }
   const int64_t quads = (p.F + 3) / 4;
-  const int64_t total = p.n_span * quads + (p.accumulate ? 0 : p.n_empty * quads);
+  const int64_t per_empty = seg_fill16(p, (int)sizeof(T), ARG) ? p.F / (16 / (int64_t)sizeof(T)) : quads;
+  const int64_t total = p.n_span * quads + (p.accumulate ? 0 : p.n_empty * per_empty);
   if (total > 0) {
     const int grid = (int)imin64(ceil_div(total, 256), (int64_t)kNumSMs * 16);
     segfinish_kernel<T, RED, ARG><<<grid, 256, 0, s>>>(p);

@@ -199,3 +199,25 @@ def csr_from_index(index, num_rows):
     rowptr = torch.zeros(num_rows + 1, dtype=torch.int64)
     rowptr[1:] = torch.cumsum(counts, 0)
     return rowptr, perm
+
+
+# ---- graph construction (torch_geometric.utils restated; fakeDatasets.py:238-259) ---------------
+def remove_self_loops(edge_index):
+    keep = [e for e in range(edge_index.shape[1]) if int(edge_index[0, e]) != int(edge_index[1, e])]
+    return edge_index[:, keep]
+
+
+def to_undirected(edge_index, num_nodes):
+    """Both directions of every edge, sorted by (row, col), duplicates removed."""
+    pairs = set()
+    for e in range(edge_index.shape[1]):
+        a, b = int(edge_index[0, e]), int(edge_index[1, e])
+        pairs.add((a, b))
+        pairs.add((b, a))
+    out = sorted(pairs)
+    return torch.tensor(out, dtype=torch.int64).t().reshape(2, -1)
+
+
+def coalesce_edges(edge_index, num_nodes):
+    out = sorted({(int(edge_index[0, e]), int(edge_index[1, e])) for e in range(edge_index.shape[1])})
+    return torch.tensor(out, dtype=torch.int64).t().reshape(2, -1)

@@ -517,3 +517,36 @@ def test_transpose_batched(cuda, outer, rows, cols, dtype):
     x = torch.arange(outer * rows * cols).view(outer, rows, cols).to(dtype)
     got = ops._transpose_batched(x.to(cuda), outer, rows, cols).view(outer, cols, rows)
     assert torch.equal(got.cpu(), x.transpose(1, 2).contiguous())
+
+
+# ---- graph construction (fakeDatasets.py:238-259: remove_self_loops → to_undirected | coalesce) --
+def test_graph_construction(cuda):
+    from gno_b200 import graph
+    g = torch.Generator().manual_seed(31)
+    n = 60
+    ei = torch.stack([torch.randint(0, n, (900,), generator=g), torch.randint(0, n, (900,), generator=g)])
+    no_loops, _ = graph.remove_self_loops(ei.to(cuda))
+    assert torch.equal(no_loops.cpu(), oracle.remove_self_loops(ei))
+    und = graph.to_undirected(no_loops, num_nodes=n)
+    assert torch.equal(und.cpu(), oracle.to_undirected(oracle.remove_self_loops(ei), n))
+    co = graph.coalesce(ei.to(cuda), num_nodes=n)
+    assert torch.equal(co.cpu(), oracle.coalesce_edges(ei, n))
+    # edge attributes ride along: both directions carry the value, duplicates add up
+    w = torch.rand(900, generator=g)
+    ui, uw = graph.to_undirected(ei.to(cuda), w.to(cuda), num_nodes=n)
+    both = torch.cat([ei, ei.flip(0)], dim=1)
+    wi, wv = oracle.coalesce(both, torch.cat([w, w]), n, n)
+    assert torch.equal(ui.cpu(), wi)
+    close(uw, wv, torch.float32)
+    # the reference's generator end to end: sorted, unique, symmetric, loop-free
+    gd = torch.Generator(device=cuda).manual_seed(5)
+    fe = graph.fake_edge_index(1000, 1000, 10, is_undirected=True, remove_loops=True, device=cuda, generator=gd)
+    key = fe[0] * 1000 + fe[1]
+    assert (key[1:] > key[:-1]).all() and (fe[0] != fe[1]).all()
+    rkey, _ = torch.sort(fe[1] * 1000 + fe[0])
+    assert torch.equal(rkey, key), "an undirected edge list equals its own transpose"
+    # collation: node ids shifted per graph, batch vector for global_mean_pool
+    e1 = torch.tensor([[0, 1], [1, 2]], device=cuda)
+    e2 = torch.tensor([[0], [1]], device=cuda)
+    bi, batch = graph.collate([e1, e2], [3, 2])
+    assert bi.tolist() == [[0, 1, 3], [1, 2, 4]] and batch.tolist() == [0, 0, 0, 1, 1]

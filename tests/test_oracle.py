@@ -167,3 +167,18 @@ def test_csr_from_index():
     rowptr, perm = oracle.csr_from_index(idx, 5)
     assert rowptr.tolist() == [0, 2, 3, 3, 6, 6]
     assert perm.tolist() == [1, 4, 3, 0, 2, 5]
+
+
+def test_graph_construction_restatement():
+    """oracle.to_undirected / coalesce_edges / remove_self_loops against a key-based torch formulation."""
+    g = torch.Generator().manual_seed(3)
+    n = 40
+    ei = torch.stack([torch.randint(0, n, (500,), generator=g), torch.randint(0, n, (500,), generator=g)])
+    nl = oracle.remove_self_loops(ei)
+    assert torch.equal(nl, ei[:, ei[0] != ei[1]])
+    both = torch.cat([nl, nl.flip(0)], dim=1)
+    key = torch.unique(both[0] * n + both[1])
+    und = oracle.to_undirected(nl, n)
+    assert torch.equal(und[0] * n + und[1], key)
+    co = oracle.coalesce_edges(ei, n)
+    assert torch.equal(co[0] * n + co[1], torch.unique(ei[0] * n + ei[1]))
