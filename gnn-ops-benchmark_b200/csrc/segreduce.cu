@@ -21,6 +21,7 @@
 // [+4 erow, +4 eid for arg, +s weight]; per row = F*s_out [+8F arg].
 #include <climits>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -187,6 +188,62 @@ __device__ __forceinline__ float finalize(float a, int e, float prev, bool mean,
   return a;
 }
 
+// Per-lane accumulator of one VB-byte vector of a row.  fp32 everywhere, except MIN/MAX over
+// 16-bit data: comparisons are exact in the storage type, so the running extremes stay packed
+// two to a register and are compared with one HSET2 per pair (the fp32 form cost five
+// instructions per element — unpack, compare, two selects — and made the bf16 max+arg kernel
+// issue-bound at 0.83 of the HBM roofline).
+template <typename T, int VB, int RED>
+struct Accum {
+  static constexpr int EPV = VB / (int)sizeof(T);
+  static constexpr bool kPacked = sizeof(T) == 2 && EPV >= 2 && (RED == GNO_MIN || RED == GNO_MAX);
+  float f[kPacked ? 1 : EPV];
+  uint32_t h[kPacked ? EPV / 2 : 1];
+
+  __device__ __forceinline__ void reset() {
+    if constexpr (kPacked) {
+      const uint32_t b = f_to_bits<T>(red_init<T, RED>()) & 0xffffu;
+#pragma unroll
+      for (int j = 0; j < EPV / 2; ++j) h[j] = b | (b << 16);
+    } else {
+#pragma unroll
+      for (int i = 0; i < EPV; ++i) f[i] = red_init<T, RED>();
+    }
+  }
+  __device__ __forceinline__ void unpack(float (&out)[EPV]) const {
+#pragma unroll
+    for (int i = 0; i < EPV; ++i) {
+      if constexpr (kPacked) out[i] = bits_to_f<T>((h[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+      else out[i] = f[i];
+    }
+  }
+};
+
+// One packed update: for each 16-bit half of val that is strictly better than the same half of
+// acc (ordered compare: NaNs never win, +0.0 and -0.0 tie), take it and record the edge id.
+// setp.{gt,lt}.{bf16x2,f16x2} yields one predicate per half; two predicated byte-permutes move
+// the winning halves, two predicated moves record the position: five instructions per pair.
+#define GNO_PACKED_UPDATE(CMP, TY)                                                         \
+  asm("{\n\t.reg .pred p, q;\n\t"                                                         \
+      "setp." CMP "." TY " p|q, %3, %0;\n\t"                                               \
+      "@p prmt.b32 %0, %0, %3, 0x3254;\n\t"                                                \
+      "@q prmt.b32 %0, %0, %3, 0x7610;\n\t"                                                \
+      "@p mov.b32 %1, %4;\n\t"                                                             \
+      "@q mov.b32 %2, %4;\n\t}"                                                            \
+      : "+r"(acc), "+r"(e_lo), "+r"(e_hi)                                                  \
+      : "r"(val), "r"(e))
+template <typename T, int RED>
+__device__ __forceinline__ void packed_update(uint32_t& acc, int& e_lo, int& e_hi, uint32_t val, int e) {
+  if constexpr (std::is_same<T, __half>::value) {
+    if constexpr (RED == GNO_MAX) GNO_PACKED_UPDATE("gt", "f16x2");
+    else GNO_PACKED_UPDATE("lt", "f16x2");
+  } else {
+    if constexpr (RED == GNO_MAX) GNO_PACKED_UPDATE("gt", "bf16x2");
+    else GNO_PACKED_UPDATE("lt", "bf16x2");
+  }
+}
+#undef GNO_PACKED_UPDATE
+
 // Write one finished (or partial) row segment held by a worker.
 template <typename T, int VB, int RED, bool ARG>
 __device__ __forceinline__ void flush_row(const SegParams& p, int row, int chunk, bool head,
@@ -249,24 +306,50 @@ __device__ __forceinline__ void flush_row(const SegParams& p, int row, int chunk
 
 // acc (+= | *= | min | max)= one gathered vector
 template <typename T, int VB, int RED, bool ARG, bool HAS_W>
-__device__ __forceinline__ void accumulate(float (&acc)[VB / (int)sizeof(T)],
+__device__ __forceinline__ void accumulate(Accum<T, VB, RED>& acc,
                                            int (&ae)[ARG ? VB / (int)sizeof(T) : 1],
                                            const Words<VB>& val, int e, float w) {
   constexpr int EPV = VB / (int)sizeof(T);
+  if constexpr (Accum<T, VB, RED>::kPacked) {
 #pragma unroll
-  for (int i = 0; i < EPV; ++i) {
-    const float f = elem<T, VB>(val, i);
-    if constexpr (RED == GNO_SUM) {
-      if constexpr (HAS_W) acc[i] = fmaf(w, f, acc[i]);
-      else acc[i] += f;
-    } else if constexpr (RED == GNO_MUL) {
-      acc[i] *= f;
-    } else {
-      if (better<RED>(f, acc[i])) {
-        acc[i] = f;
-        if constexpr (ARG) ae[i] = e;
+    for (int j = 0; j < EPV / 2; ++j) {
+      if constexpr (ARG) {
+        packed_update<T, RED>(acc.h[j], ae[2 * j], ae[2 * j + 1], val.w[j], e);
+      } else {
+        int lo = 0, hi = 0;
+        packed_update<T, RED>(acc.h[j], lo, hi, val.w[j], e);
       }
     }
+  } else {
+#pragma unroll
+    for (int i = 0; i < EPV; ++i) {
+      const float f = elem<T, VB>(val, i);
+      if constexpr (RED == GNO_SUM) {
+        if constexpr (HAS_W) acc.f[i] = fmaf(w, f, acc.f[i]);
+        else acc.f[i] += f;
+      } else if constexpr (RED == GNO_MUL) {
+        acc.f[i] *= f;
+      } else {
+        if (better<RED>(f, acc.f[i])) {
+          acc.f[i] = f;
+          if constexpr (ARG) ae[i] = e;
+        }
+      }
+    }
+  }
+}
+
+// flush_row on an Accum (unpacks the packed 16-bit extremes; row boundaries are rare next to edges)
+template <typename T, int VB, int RED, bool ARG>
+__device__ __forceinline__ void flush_acc(const SegParams& p, int row, int chunk, bool head, bool tail,
+                                          int seg_len, int v, const Accum<T, VB, RED>& acc,
+                                          const int (&ae)[ARG ? VB / (int)sizeof(T) : 1]) {
+  if constexpr (Accum<T, VB, RED>::kPacked) {
+    float f[VB / (int)sizeof(T)];
+    acc.unpack(f);
+    flush_row<T, VB, RED, ARG>(p, row, chunk, head, tail, seg_len, v, f, ae);
+  } else {
+    flush_row<T, VB, RED, ARG>(p, row, chunk, head, tail, seg_len, v, acc.f, ae);
   }
 }
 
@@ -298,10 +381,9 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
   const int32_t* eid = p.eid ? p.eid + k0 : nullptr;
   const T* wgt = HAS_W ? static_cast<const T*>(p.w) + k0 : nullptr;
 
-  float acc[EPV];
+  Accum<T, VB, RED> acc;
   int ae[ARG ? EPV : 1];
-#pragma unroll
-  for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
+  acc.reset();
   if constexpr (ARG) {
 #pragma unroll
     for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
@@ -369,12 +451,11 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
           if (row_u != cur_row) {  // the previous row ended inside this chunk
             const int kk = t + j + u;
             if (vact)
-              flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, false, kk - seg_start, v, acc, ae);
+              flush_acc<T, VB, RED, ARG>(p, cur_row, chunk, head, false, kk - seg_start, v, acc, ae);
             head = false;
             cur_row = row_u;
             seg_start = kk;
-#pragma unroll
-            for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
+            acc.reset();
             if constexpr (ARG) {
 #pragma unroll
               for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
@@ -410,12 +491,11 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
         if (row_u != cur_row) {
           const int kk = t + slot;
           if (vact)
-            flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, false, kk - seg_start, v, acc, ae);
+            flush_acc<T, VB, RED, ARG>(p, cur_row, chunk, head, false, kk - seg_start, v, acc, ae);
           head = false;
           cur_row = row_u;
           seg_start = kk;
-#pragma unroll
-          for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
+          acc.reset();
           if constexpr (ARG) {
 #pragma unroll
             for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
@@ -428,7 +508,7 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
   }
   if (vact && nv > 0) {
     const bool tail = (k0 + nv < p.E) && (__ldg(erow + nv) == cur_row);
-    flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, tail, nv - seg_start, v, acc, ae);
+    flush_acc<T, VB, RED, ARG>(p, cur_row, chunk, head, tail, nv - seg_start, v, acc, ae);
   }
 }
 
@@ -537,10 +617,9 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
   const bool has_idx = p.gidx != nullptr;
   const bool e_is_k = ARG && !sep_e && !(p.eid && p.eid == p.gidx);  // eid == NULL: edge id = k
 
-  float acc[EPV];
+  Accum<T, VB, RED> acc;
   int ae[ARG ? EPV : 1];
-#pragma unroll
-  for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
+  acc.reset();
   if constexpr (ARG) {
 #pragma unroll
     for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
@@ -550,12 +629,11 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
   int seg_start = 0;
 
   auto close_row = [&](int new_row, int kk) {
-    flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, false, kk - seg_start, v, acc, ae);
+    flush_acc<T, VB, RED, ARG>(p, cur_row, chunk, head, false, kk - seg_start, v, acc, ae);
     head = false;
     cur_row = new_row;
     seg_start = kk;
-#pragma unroll
-    for (int i = 0; i < EPV; ++i) acc[i] = red_init<T, RED>();
+    acc.reset();
     if constexpr (ARG) {
 #pragma unroll
       for (int i = 0; i < EPV; ++i) ae[i] = kNoArg;
@@ -600,7 +678,7 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
   if (nv > 0) {
     const bool tail = (k0 + nv < p.E) &&
                       ((soff + nv < n) ? rowp[nv] : __ldg(p.erow + k0 + nv)) == cur_row;
-    flush_row<T, VB, RED, ARG>(p, cur_row, chunk, head, tail, nv - seg_start, v, acc, ae);
+    flush_acc<T, VB, RED, ARG>(p, cur_row, chunk, head, tail, nv - seg_start, v, acc, ae);
   }
 }
 
