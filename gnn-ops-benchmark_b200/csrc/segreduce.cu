@@ -6,11 +6,14 @@
 // of chunk_len edges; a worker (a group of G lanes, G*VB bytes >= one feature
 // row, or a full warp per 32-vector column tile for wide rows) owns one chunk,
 // so every worker moves the same number of bytes no matter how skewed the
-// degrees are (power-law graphs need no special case).  A worker stages G
-// sorted-edge records (gather index, destination row, edge id, weight) in its
-// lanes with one coalesced request per array, broadcasts them by shuffle,
-// keeps U independent VB-byte (16/8/4/2 by alignment) feature-row loads in
-// flight, and accumulates in fp32.  When the destination row changes it
+// degrees are (power-law graphs need no special case).  The edge records of a
+// CTA's workers (gather index, destination row, edge id, weight) are one
+// contiguous slab per array, staged in shared memory by 1-D TMA bulk copies
+// (segreduce_staged_kernel; workers narrower than 16 lanes stage them in
+// registers and broadcast by shuffle, segreduce_kernel).  A worker keeps U
+// independent VB-byte (16/8/4/2 by alignment) feature-row loads in flight and
+// accumulates in fp32 (MIN/MAX over 16-bit data stay packed in the storage
+// type: comparisons are exact there).  When the destination row changes it
 // writes the finished row; the rows cut by a chunk boundary go to a partial
 // buffer (two slots per chunk) and are combined IN CHUNK ORDER by
 // segfinish_kernel, which also zero-fills empty rows.  No atomics anywhere:

@@ -2,10 +2,10 @@
 //
 // Per pass: (1) per-tile digit histogram, (2) device-wide exclusive scan of
 // the digit-major count matrix, (3) scatter: every 256-thread block ranks a
-// 4096-key sub-tile entirely on chip — warp-level __match_any ranking into
-// per-warp shared-memory histograms, a cross-warp/cross-digit scan, a
-// shared-memory exchange into sorted order — then writes runs of equal
-// digits to consecutive global addresses.  Order inside a sub-tile is
+// 4096-key sub-tile entirely on chip — warp-level match-by-ballot ranking (one
+// ballot per digit bit) into per-warp shared-memory histograms, a
+// cross-warp/cross-digit scan, a shared-memory exchange into sorted order —
+// then writes runs of equal digits to consecutive global addresses.  Order inside a sub-tile is
 // (warp, item, lane) == ascending input index, so the sort is stable.
 //
 // HBM-bound integer work: per pass it reads keys twice and payload once and
