@@ -2,8 +2,9 @@
 __graft_entry__.smoke() and bench.py's CPU-baseline legs.  NOT product code.
 
 PARITY UNPINNED for the torch_scatter / torch_sparse semantics (the upstream
-packages are absent; see oracle.c); pinned against tests/golden/*.npz for the
-native torch ops the reference scripts call.
+packages are absent; see oracle.c) beyond the four worked examples their
+READMEs publish (tests/golden/upstream_published.py); pinned against
+tests/golden/*.npz for the native torch ops the reference scripts call.
 
 All functions take and return torch CPU tensors.  Half / bfloat16 inputs are
 widened to float32, reduced in float32 and rounded once on return.

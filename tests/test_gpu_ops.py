@@ -550,3 +550,29 @@ def test_graph_construction(cuda):
     e2 = torch.tensor([[0], [1]], device=cuda)
     bi, batch = graph.collate([e1, e2], [3, 2])
     assert bi.tolist() == [[0, 1, 3], [1, 2, 4]] and batch.tolist() == [0, 0, 0, 1, 1]
+
+
+# ---- known-answer vectors published by the upstream packages (READMEs) ---------------------------
+def test_upstream_published_examples(cuda):
+    """scatter_max (pytorch_scatter README) and coalesce / transpose / spmm (pytorch_sparse README)
+    through the shim packages on the GPU; tests/golden/upstream_published.py."""
+    import importlib.util
+    import os
+    import torch_scatter
+    import torch_sparse
+    spec = importlib.util.spec_from_file_location(
+        "upstream_published", os.path.join(os.path.dirname(__file__), "golden", "upstream_published.py"))
+    up = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(up)
+    v = up.SCATTER_MAX
+    out, arg = torch_scatter.scatter_max(v["src"].to(cuda), v["index"].to(cuda), dim=-1)
+    assert torch.equal(out.cpu(), v["out"]) and torch.equal(arg.cpu(), v["arg"])
+    v = up.COALESCE
+    i, val = torch_sparse.coalesce(v["index"].to(cuda), v["value"].to(cuda), m=v["m"], n=v["n"])
+    assert torch.equal(i.cpu(), v["out_index"]) and torch.equal(val.cpu(), v["out_value"])
+    v = up.TRANSPOSE
+    i, val = torch_sparse.transpose(v["index"].to(cuda), v["value"].to(cuda), v["m"], v["n"])
+    assert torch.equal(i.cpu(), v["out_index"]) and torch.equal(val.cpu(), v["out_value"])
+    v = up.SPMM
+    out = torch_sparse.spmm(v["index"].to(cuda), v["value"].to(cuda), v["m"], v["n"], v["matrix"].to(cuda))
+    assert torch.equal(out.cpu(), v["out"])

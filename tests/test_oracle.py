@@ -182,3 +182,23 @@ def test_graph_construction_restatement():
     assert torch.equal(und[0] * n + und[1], key)
     co = oracle.coalesce_edges(ei, n)
     assert torch.equal(co[0] * n + co[1], torch.unique(ei[0] * n + ei[1]))
+
+
+def test_oracle_matches_upstream_published_examples():
+    """The worked examples of the pytorch_scatter / pytorch_sparse READMEs (tests/golden/upstream_published.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "upstream_published", os.path.join(os.path.dirname(__file__), "golden", "upstream_published.py"))
+    up = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(up)
+    v = up.SCATTER_MAX
+    out, arg = oracle.scatter(v["src"], v["index"], -1, None, "max")
+    assert torch.equal(out, v["out"]) and torch.equal(arg, v["arg"])
+    v = up.COALESCE
+    i, val = oracle.coalesce(v["index"], v["value"], v["m"], v["n"])
+    assert torch.equal(i, v["out_index"]) and torch.equal(val, v["out_value"])
+    v = up.TRANSPOSE
+    i, val = oracle.transpose(v["index"], v["value"], v["m"], v["n"])
+    assert torch.equal(i, v["out_index"]) and torch.equal(val, v["out_value"])
+    v = up.SPMM
+    assert torch.equal(oracle.spmm(v["index"], v["value"], v["m"], v["n"], v["matrix"]), v["out"])
