@@ -170,3 +170,18 @@ def test_sass_carries_the_claimed_instructions():
     assert "HSETP2.BF16" in mx, "packed bf16 compare missing from the max kernel"
     srt = _sass(r"radix_scatter_kernelIjjLb1")
     assert "VOTE" in srt
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/gno_b200.h is the drop-in boundary: it must compile as C99 with no CUDA or torch
+    header in sight (a cgo / ctypes / JNI binding sees exactly this file)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "gno_b200.h"\nint main(void) { gno_csr g; (void)g; return gno_abi_version() > 0; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
