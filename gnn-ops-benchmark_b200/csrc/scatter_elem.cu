@@ -12,6 +12,11 @@
 
 namespace gno {
 
+// scatter_onchip.cu: one-launch shared-memory path (returns -1 when the shape does not fit it)
+int scatter_onchip(const void* src, const int64_t* index, int64_t B, int64_t E, int64_t K, void* out,
+                   int64_t* arg, int64_t N, int dtype, int reduce, int accumulate, cudaStream_t s);
+bool scatter_onchip_ok(int64_t B, int64_t E, int64_t K, int64_t N, int dtype, int reduce);
+
 static unsigned grid_for_elems(int64_t n) {
   int64_t b = ceil_div(n, 256);
   int64_t cap = (int64_t)kNumSMs * 32;
@@ -243,11 +248,15 @@ using namespace gno;
 
 extern "C" {
 
-int gno_scatter_elementwise_workspace(int64_t B, int64_t N, int64_t K, int dtype, int reduce,
+int gno_scatter_elementwise_workspace(int64_t B, int64_t E, int64_t N, int64_t K, int dtype, int reduce,
                                       size_t* bytes) {
-  GNO_CHECK_ARG(bytes && B >= 0 && N >= 0 && K >= 0, "gno_scatter_elementwise_workspace: bad argument");
+  GNO_CHECK_ARG(bytes && B >= 0 && E >= 0 && N >= 0 && K >= 0, "gno_scatter_elementwise_workspace: bad argument");
   const int64_t n_out = B * N * K;
   WorkspaceSizer sz;
+  if (scatter_onchip_ok(B, E, K, N, dtype, reduce)) {  // bins live in shared memory: no workspace
+    *bytes = 0;
+    return GNO_OK;
+  }
   if (reduce == GNO_MIN || reduce == GNO_MAX) {
     sz.take<uint32_t>((size_t)n_out);
     sz.take<long long>((size_t)n_out);
@@ -260,14 +269,24 @@ int gno_scatter_elementwise_workspace(int64_t B, int64_t N, int64_t K, int dtype
 }
 
 int gno_scatter_elementwise(const void* src, const int64_t* index, int64_t B, int64_t E, int64_t K,
-                            void* out, int64_t* arg, int64_t N, int dtype, int reduce, void* ws,
-                            size_t ws_bytes, gno_stream_t stream) {
+                            void* out, int64_t* arg, int64_t N, int dtype, int reduce, int accumulate,
+                            void* ws, size_t ws_bytes, gno_stream_t stream) {
   GNO_CHECK_ARG(B >= 0 && E >= 0 && K >= 0 && N >= 0, "gno_scatter_elementwise: negative size");
   GNO_CHECK_ARG(reduce >= GNO_SUM && reduce <= GNO_MAX, "gno_scatter_elementwise: unknown reduce %d", reduce);
   GNO_CHECK_ARG(arg == nullptr || reduce == GNO_MIN || reduce == GNO_MAX,
                 "gno_scatter_elementwise: arg output only for MIN/MAX");
   if (B * N * K == 0) return GNO_OK;
   GNO_CHECK_ARG(out && (B * E * K == 0 || (src && index)), "gno_scatter_elementwise: NULL buffer");
+  GNO_CHECK_ARG(dtype == GNO_F32 || dtype == GNO_F16 || dtype == GNO_BF16,
+                "gno_scatter_elementwise: unknown dtype %d", dtype);
+  if (B * E * K > 0) {
+    const int rc = scatter_onchip(src, index, B, E, K, out, arg, N, dtype, reduce, accumulate,
+                                  (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
+  if (accumulate)
+    return fail(GNO_ERR_UNSUPPORTED, "gno_scatter_elementwise: accumulate needs the on-chip path "
+                "(N too large for shared-memory bins, or an empty input)");
   ElemShape sh{B, E, K, N, K};
   // column-blocked traversal when the accumulator slice of one row-major sweep exceeds ~24 MB
   if (K >= 64 && N * K * 4 > (int64_t(24) << 20)) {

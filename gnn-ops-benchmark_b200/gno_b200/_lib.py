@@ -72,10 +72,10 @@ PROTOTYPES = {
                               POINTER(c_int64), POINTER(c_int64), c_int64, c_int64, c_void_p]),
     "gno_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p,
                                 c_void_p]),
-    "gno_scatter_elementwise_workspace": (c_int, [c_int64, c_int64, c_int64, c_int, c_int,
+    "gno_scatter_elementwise_workspace": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int, c_int,
                                                   POINTER(c_size_t)]),
     "gno_scatter_elementwise": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
-                                        c_void_p, c_int64, c_int, c_int, c_void_p, c_size_t,
+                                        c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_size_t,
                                         c_void_p]),
     "gno_coalesce_workspace": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int,
                                        POINTER(c_size_t)]),
@@ -97,7 +97,7 @@ def _load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.gno_abi_version() != 1:
+    if lib.gno_abi_version() != 2:
         raise GnoError("libgno_b200.so ABI version mismatch")
     return lib
 

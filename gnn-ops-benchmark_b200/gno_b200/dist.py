@@ -31,6 +31,25 @@ def edge_balanced_ranges(row_counts, world):
     return torch.cummax(bounds, 0).values  # monotone even for degenerate inputs
 
 
+def stage_ranges(row_costs, stages, fracs=None):
+    """Cut rows [0, n) into `stages` contiguous sub-ranges whose summed cost follows `fracs`
+    (default: equal shares).  Returns int64 [stages + 1] boundaries on row_costs' device."""
+    n = row_costs.numel()
+    if fracs is None:
+        fracs = [1.0 / stages] * stages
+    if len(fracs) != stages or min(fracs) < 0 or sum(fracs) <= 0:
+        raise ValueError("stage_fracs must hold one non-negative share per stage")
+    dev = row_costs.device
+    csum = torch.cumsum(row_costs.to(torch.float64), 0)
+    total = float(csum[-1]) if n else 0.0
+    cum = torch.cumsum(torch.tensor(fracs, dtype=torch.float64), 0)[:-1] / sum(fracs)
+    cuts = (torch.searchsorted(csum, (cum * total).to(dev), right=False) + 1).clamp_(max=n) if n else \
+        torch.zeros(stages - 1, dtype=torch.int64, device=dev)
+    bounds = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), cuts.to(torch.int64),
+                        torch.full((1,), n, dtype=torch.int64, device=dev)])
+    return torch.cummax(bounds, 0).values
+
+
 def partition_graph(src, dst, num_nodes, world):
     """Split a global edge list into per-rank shards by destination range.
 
@@ -59,7 +78,8 @@ class DistAggregator:
     """
 
     def __init__(self, bounds, src_global, dst_local, rank=None, world=None, group=None, stages=1,
-                 feature_bounds=None, exchange="allgather", cyclic_rows=None):
+                 feature_bounds=None, exchange="allgather", cyclic_rows=None, stage_fracs=None,
+                 row_weight=0):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -87,9 +107,13 @@ class DistAggregator:
             b = self.xbounds.to(src_global.device)
             owner = torch.searchsorted(b[1:].contiguous(), src_global, right=True)
             local = src_global - b[owner]
+        if exchange in ("needed", "push"):
+            # needed-rows exchanges pipeline over DESTINATION sub-ranges (see _setup_needed)
+            self.xstages, stages = max(1, int(stages)), 1
+            self.stage_fracs, self.row_weight = stage_fracs, int(row_weight)
         self.stages = max(1, min(int(stages), max(self.max_rows, 1)))
         # single-stage layout: row of the padded gather buffer [P * max_rows, F]
-        self.src_padded = owner * self.max_rows + local
+        self.src_padded = owner * self.max_rows + local if exchange in ("allgather", "allgather_push") else None
         # K-stage layout: chunk c holds rows [c*mc, c*mc + rows_c) of every shard
         self.mc = -(-self.max_rows // self.stages) if self.max_rows else 1
         self.stage_rows = [max(0, min(self.mc, self.max_rows - c * self.mc)) for c in range(self.stages)]
@@ -103,6 +127,8 @@ class DistAggregator:
         self._plan = None
         self._gidx = None
         self._stage_plans = None
+        self._push_stream = None
+        self._push_events = None
         self.exchange_mode = exchange
         if exchange in ("needed", "push"):
             self._setup_needed(src_global, owner, local)
@@ -113,70 +139,117 @@ class DistAggregator:
         elif exchange != "allgather":
             raise ValueError("exchange must be 'allgather', 'allgather_push', 'needed' or 'push'")
 
-    # -- needed-rows-only exchange -------------------------------------------
+    # -- needed-rows-only exchange, pipelined over destination sub-ranges ------
     def _setup_needed(self, src_global, owner, local):
         """Skewed graphs reference only a fraction of the feature rows from each rank (RMAT-26 at
         P=4: 26 %).  Each rank asks every owner for exactly the rows its edges read; per call the
-        owners gather those rows and one all-to-all delivers them, already in the order of the
-        sorted distinct source ids, so the gather index is just the rank of the id."""
+        owners gather those rows and deliver them in the order of the receiver's gather buffer, so
+        the gather index of an edge is just the position of its source in that buffer.
+
+        K > 1 stages: this rank's destination rows are cut into K contiguous sub-ranges (stage s
+        reduces sub-range s); a needed source row belongs to the FIRST stage whose edges read it,
+        and the receive buffer is laid out stage-major, owner-minor.  Stage s of the exchange then
+        delivers exactly the rows stage s of the reduction is still missing, so the reduction of
+        sub-range s can run while the rows of s+1 are in flight — without splitting any output row
+        (every row is written once, by one stage: no accumulate pass, no extra rounding)."""
+        P, K = self.world, self.xstages
+        dev = src_global.device
         key = owner * self.max_rows + local                      # ascending key = grouped by owner
         uniq, inv = torch.unique(key, return_inverse=True)
         uowner = torch.div(uniq, self.max_rows, rounding_mode="floor")
-        recv_counts = torch.bincount(uowner, minlength=self.world)
         req = uniq - uowner * self.max_rows                        # row inside the owner's shard
-        if self.world > 1:
-            send_counts = torch.empty_like(recv_counts)
-            dist.all_to_all_single(send_counts, recv_counts, group=self.group)
-            self.send_splits = [int(v) for v in send_counts.tolist()]
-            self.recv_splits = [int(v) for v in recv_counts.tolist()]
-            serve = torch.empty(sum(self.send_splits), dtype=torch.int64, device=req.device)
-            dist.all_to_all_single(serve, req, self.send_splits, self.recv_splits, group=self.group)
+        n_u = int(uniq.numel())
+        if K > 1:
+            counts = torch.bincount(self.dst_local, minlength=self.n_out) + self.row_weight
+            self.sub_bounds = stage_ranges(counts, K, self.stage_fracs).cpu()
+            sb = self.sub_bounds.to(dev)
+            stage_e = torch.searchsorted(sb[1:].contiguous(), self.dst_local, right=True).clamp_(max=K - 1)
+            first = torch.full((n_u,), K - 1, dtype=torch.int64, device=dev)
+            first.scatter_reduce_(0, inv, stage_e, "amin", include_self=True)
+            self.stage_of_edge = stage_e
         else:
-            self.send_splits = self.recv_splits = [int(uniq.numel())]
-            serve = req
-        self.serve_rows = serve          # local rows this rank sends, grouped by requester
-        self.n_needed = int(uniq.numel())
-        self.src_needed = inv            # per-edge row of the received buffer
+            self.sub_bounds = torch.tensor([0, self.n_out], dtype=torch.int64)
+            first = torch.zeros(n_u, dtype=torch.int64, device=dev)
+            self.stage_of_edge = None
+        # receive layout: stage-major, owner-minor, ascending row id inside (uniq is sorted)
+        order = torch.argsort(first * P + uowner, stable=True)
+        pos = torch.empty_like(order)
+        pos[order] = torch.arange(n_u, dtype=torch.int64, device=dev)
+        self.src_needed = pos[inv]                                 # per-edge row of the receive buffer
+        self.n_needed = n_u
+        cnt = torch.bincount(first * P + uowner, minlength=K * P).view(K, P)  # rows I receive [stage, owner]
+        self.recv_cnt = [[int(v) for v in row] for row in cnt.tolist()]
+        flat = cnt.flatten()
+        roff = torch.cumsum(flat, 0) - flat                        # where each (stage, owner) block starts
+        self.recv_off = [[int(v) for v in row] for row in roff.view(K, P).tolist()]
+        self.stage_row0 = [self.recv_off[s][0] for s in range(K)] + [n_u]
+        self.recv_splits = [int(v) for v in cnt.sum(0).tolist()]   # per owner, all stages
+        # requests travel grouped by owner (stage-minor inside)
+        order_o = torch.argsort(uowner * K + first, stable=True)
+        req_by_owner = req[order_o].contiguous()
+        if P > 1:
+            want_cnt = cnt.t().contiguous()                         # [owner, stage]
+            serve_cnt = torch.empty_like(want_cnt)                  # [requester, stage]
+            dist.all_to_all_single(serve_cnt, want_cnt, group=self.group)
+            want_off = roff.view(K, P).t().contiguous()
+            put_off = torch.empty_like(want_off)                    # [requester, stage]: where my rows land there
+            dist.all_to_all_single(put_off, want_off, group=self.group)
+            self.send_splits = [int(v) for v in serve_cnt.sum(1).tolist()]
+            serve = torch.empty(sum(self.send_splits), dtype=torch.int64, device=dev)
+            dist.all_to_all_single(serve, req_by_owner, self.send_splits, self.recv_splits, group=self.group)
+        else:
+            serve_cnt, put_off = cnt.t().contiguous(), roff.view(K, P).t().contiguous()
+            self.send_splits = list(self.recv_splits)
+            serve = req_by_owner
+        # serve list: stage-major, requester-minor (it arrived requester-major, stage-minor)
+        sc = serve_cnt.flatten()                                     # block sizes in arrival order (q, s)
+        blk_q = torch.arange(P, device=dev).repeat_interleave(K)
+        blk_s = torch.arange(K, device=dev).repeat(P)
+        tag = torch.repeat_interleave(blk_s * P + blk_q, sc)
+        self.serve_rows = serve[torch.argsort(tag, stable=True)].contiguous()
+        sc_sq = serve_cnt.t().contiguous()                           # [stage, requester]
+        self.serve_cnt = [[int(v) for v in row] for row in sc_sq.tolist()]
+        self.serve_stage0 = [0]
+        for s_ in range(K):
+            self.serve_stage0.append(self.serve_stage0[-1] + sum(self.serve_cnt[s_]))
+        self.put_off = [[int(v) for v in row] for row in put_off.t().tolist()]  # [stage][requester]
 
-    def exchange_needed(self, x_local, out=None, gather_rows=None):
-        """Gather the rows other ranks asked for and deliver them with one all-to-all.
-        gather_rows(x, rows) defaults to the CUDA row-gather kernel (gno_gather_rows); the gloo
-        host-logic tests inject their own, the product has no CPU path."""
+    def _stage_serve(self, s):
+        return self.serve_rows[self.serve_stage0[s]:self.serve_stage0[s + 1]]
+
+    def exchange_needed(self, x_local, out=None, gather_rows=None, stage=None, async_op=False):
+        """Gather the rows other ranks asked for and deliver them with one all-to-all per stage
+        (all stages when stage is None).  gather_rows(x, rows) defaults to the CUDA row-gather
+        kernel (gno_gather_rows); the gloo host-logic tests inject their own, the product has no
+        CPU path.  Returns the receive buffer (and the list of async works with async_op)."""
         if x_local.size(0) != self.n_local:
             raise ValueError("x_local must hold this rank's rows")
         if gather_rows is None:
             from . import ops
-            send = ops.index_select(x_local, 0, self.serve_rows)
-        else:
-            send = gather_rows(x_local, self.serve_rows)
-        if self.world == 1:
-            return send
+            gather_rows = lambda x, rows: ops.index_select(x, 0, rows)  # noqa: E731
         if out is None:
             out = torch.empty((self.n_needed, x_local.size(1)), dtype=x_local.dtype, device=x_local.device)
-        dist.all_to_all_single(out, send, self.recv_splits, self.send_splits, group=self.group)
-        return out
+        works = []
+        for s in (range(self.xstages) if stage is None else [stage]):
+            send = gather_rows(x_local, self._stage_serve(s))
+            dst = out[self.stage_row0[s]:self.stage_row0[s + 1]]
+            if self.world == 1:
+                dst.copy_(send)
+                continue
+            w = dist.all_to_all_single(dst, send, self.recv_cnt[s], self.serve_cnt[s], group=self.group,
+                                       async_op=async_op)
+            works.append(w)
+        return (out, works) if async_op else out
 
     # -- needed rows pushed over NVLink by the gather kernel itself -----------------------------
     def _setup_push(self):
         """exchange="push": the owners' gather kernel stores each requested row straight into the
         requester's receive buffer through NVLink peer pointers (torch symmetric memory), instead
-        of gathering into a send buffer and calling an all-to-all.  Every owner needs to know where
-        its rows start inside each requester's buffer."""
-        dev = self.serve_rows.device
-        recv_off = torch.zeros(self.world, dtype=torch.int64)
-        recv_off[1:] = torch.cumsum(torch.tensor(self.recv_splits[:-1], dtype=torch.int64), 0)
-        recv_off = recv_off.to(dev)
-        row_off = torch.empty_like(recv_off)
-        n_max = torch.tensor([self.n_needed], dtype=torch.int64, device=dev)
+        of gathering into a send buffer and calling an all-to-all.  _setup_needed already told
+        every owner where its rows start inside each requester's buffer (put_off)."""
+        n_max = torch.tensor([self.n_needed], dtype=torch.int64, device=self.serve_rows.device)
         if self.world > 1:
-            dist.all_to_all_single(row_off, recv_off, group=self.group)
             dist.all_reduce(n_max, op=dist.ReduceOp.MAX, group=self.group)
-        else:
-            row_off.copy_(recv_off)
-        self._push_row_off = [int(v) for v in row_off.tolist()]
-        self._push_seg = [0]
-        for c in self.send_splits:
-            self._push_seg.append(self._push_seg[-1] + c)
         self._push_rows_max = max(int(n_max.item()), 1)
         self._push_bufs = {}
 
@@ -189,28 +262,42 @@ class DistAggregator:
             t = symm.empty((self._push_rows_max, F), dtype=dtype, device=device)
             hdl = symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
             ptrs = (ctypes.c_void_p * self.world)(*[int(hdl.buffer_ptrs[q]) for q in range(self.world)])
-            seg = (ctypes.c_int64 * (self.world + 1))(*self._push_seg)
-            off = (ctypes.c_int64 * self.world)(*self._push_row_off)
-            st = self._push_bufs[key] = (t, hdl, ptrs, seg, off)
+            stages = []
+            for s in range(self.xstages):
+                seg = [0]
+                for c in self.serve_cnt[s]:
+                    seg.append(seg[-1] + c)
+                stages.append(((ctypes.c_int64 * (self.world + 1))(*seg),
+                               (ctypes.c_int64 * self.world)(*self.put_off[s]), seg))
+            st = self._push_bufs[key] = (t, hdl, ptrs, stages)
         return st
 
-    def exchange_push(self, x_local):
-        import ctypes
+    def _push_stage(self, x_local, st, s):
+        """Launch stage s of the exchange on the current stream: one kernel that reads every row a
+        peer needs for its stage s once from local HBM and stores it into that peer's buffer."""
         from ._lib import check, lib
         from .plan import _ptr, _stream
+        t, hdl, ptrs, stages = st
+        seg_c, off_c, seg = stages[s]
+        rows = self._stage_serve(s)
+        F, es = x_local.size(1), x_local.element_size()
+        with torch.cuda.device(x_local.device):
+            check(lib.gno_push_rows(_ptr(x_local), F * es, x_local.stride(0) * es, _ptr(rows),
+                                    rows.numel(), self.world, ptrs, seg_c, off_c, F * es,
+                                    seg[(self.rank + 1) % self.world], _stream(x_local.device)))
+
+    def exchange_push(self, x_local):
+        """All stages back to back on the current stream (no overlap); returns the receive buffer."""
         if x_local.size(0) != self.n_local:
             raise ValueError("x_local must hold this rank's rows")
         x_local = x_local.contiguous()
-        F, es = x_local.size(1), x_local.element_size()
-        t, hdl, ptrs, seg, off = self._push_buffer(F, x_local.dtype, x_local.device)
+        st = self._push_buffer(x_local.size(1), x_local.dtype, x_local.device)
+        hdl = st[1]
         hdl.barrier(channel=0)  # every peer is done reading its buffer from the previous call
-        with torch.cuda.device(x_local.device):
-            check(lib.gno_push_rows(_ptr(x_local), F * es, x_local.stride(0) * es, _ptr(self.serve_rows),
-                                    self.serve_rows.numel(), self.world, ptrs, seg, off, F * es,
-                                    self._push_seg[(self.rank + 1) % self.world],
-                                    _stream(x_local.device)))
+        for s in range(self.xstages):
+            self._push_stage(x_local, st, s)
         hdl.barrier(channel=1)  # every row has landed everywhere
-        return t[:self.n_needed]
+        return st[0][:self.n_needed]
 
     # -- all-gather by peer stores ---------------------------------------------------------------
     def exchange_allgather_push(self, x_local):
@@ -301,9 +388,80 @@ class DistAggregator:
                 self._stage_plans.append((p, p.sorted_ids(ids)))
         return self._stage_plans
 
+    def xstage_plans(self):
+        """needed / push exchange with K destination stages: one plan per destination sub-range
+        [(plan, gidx, eid, row_lo, row_hi)]; eid maps a sorted edge of the sub-range back to its
+        position in this rank's edge list (the arg outputs)."""
+        if self._stage_plans is None:
+            from . import plan as planmod
+            self._stage_plans = []
+            for s in range(self.xstages):
+                lo, hi = int(self.sub_bounds[s]), int(self.sub_bounds[s + 1])
+                if self.xstages == 1:
+                    p, gidx = self.plan()
+                    self._stage_plans.append((p, gidx, p.perm, lo, hi))
+                    continue
+                where = torch.nonzero(self.stage_of_edge == s).flatten()
+                p = planmod.build_plan(self.dst_local[where] - lo, hi - lo)
+                gidx = p.sorted_ids(self.src_needed[where])
+                eid = p.sorted_ids(where)
+                self._stage_plans.append((p, gidx, eid, lo, hi))
+        return self._stage_plans
+
+    def _aggregate_staged(self, x_local, reduce, want_arg, x_full, out):
+        """K-stage needed-rows exchange overlapped with the reduction (exchange = push | needed).
+
+        Stage s of the exchange delivers the rows destination sub-range s still misses; the
+        reduction of sub-range s runs as soon as they have landed, while stage s+1 is in flight.
+        The exchange runs on a second, high-priority stream so its CTAs take SM slots as
+        reduction CTAs retire instead of queueing behind the whole launch."""
+        from . import ops
+        dev = x_local.device
+        F = x_local.size(1)
+        plans = self.xstage_plans()
+        x_local = x_local.contiguous()
+        if out is None:
+            out = torch.empty((self.n_out, F), dtype=x_local.dtype, device=dev)
+        arg = torch.empty((self.n_out, F), dtype=torch.int64, device=dev) if want_arg else None
+        cur = torch.cuda.current_stream(dev)
+        if self._push_stream is None:
+            self._push_stream = torch.cuda.Stream(dev, priority=-1)
+            self._push_events = [torch.cuda.Event() for _ in range(self.xstages + 1)]
+        ps, ev = self._push_stream, self._push_events
+        ev[-1].record(cur)        # x_local is ready and the previous call's reduction has been issued
+        ps.wait_event(ev[-1])
+        push = self.exchange_mode == "push"
+        if push:
+            st = self._push_buffer(F, x_local.dtype, dev)
+            recv, hdl = st[0][:self.n_needed], st[1]
+        else:
+            recv = x_full if x_full is not None else torch.empty((self.n_needed, F), dtype=x_local.dtype, device=dev)
+        with torch.cuda.stream(ps):
+            if push:
+                hdl.barrier(channel=0)      # every peer is done reading its buffer from the previous call
+            for s in range(self.xstages):
+                if push:
+                    self._push_stage(x_local, st, s)
+                    hdl.barrier(channel=1)  # stage s has landed everywhere
+                else:
+                    self.exchange_needed(x_local, recv, stage=s)
+                ev[s].record(ps)
+        for s, (p, gidx, eid, lo, hi) in enumerate(plans):
+            cur.wait_event(ev[s])
+            if hi == lo:
+                continue
+            r = ops.segment_reduce(p, recv, reduce, gidx=gidx, eid=eid, want_arg=want_arg,
+                                   arg_fill=self.dst_local.numel(), out=out[lo:hi])
+            if want_arg:
+                arg[lo:hi].copy_(r[1])
+        return (out, arg) if want_arg else out
+
     def aggregate(self, x_local, reduce="sum", return_arg=False, x_full=None, out=None, stage_bufs=None):
         """out[range_r] = reduce over local edges of x_global[src]; arg = local edge position."""
         from . import ops
+        want_arg = return_arg and reduce in ("min", "max")
+        if self.exchange_mode in ("needed", "push") and self.xstages > 1:
+            return self._aggregate_staged(x_local, reduce, want_arg, x_full, out)
         if self.stages > 1 and reduce in ("sum", "mean") and not return_arg and \
                 self.exchange_mode == "allgather":
             plans = self.stage_plans()
@@ -328,6 +486,5 @@ class DistAggregator:
             xf = self.exchange_needed(x_local, x_full)
         else:
             xf = self.exchange(x_local, x_full)
-        want_arg = return_arg and reduce in ("min", "max")
         return ops.segment_reduce(plan, xf, reduce, gidx=gidx, eid=plan.perm, want_arg=want_arg,
                                   arg_fill=plan.E, out=out)

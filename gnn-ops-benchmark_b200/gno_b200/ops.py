@@ -46,7 +46,7 @@ _memo_store = collections.OrderedDict()
 
 def _memo(kind, t, extra, builder, capacity=8):
     """Small LRU keyed on a tensor's identity/version (keeps the tensor alive)."""
-    key = (kind, t.data_ptr(), t._version, t.numel(), str(t.device)) + tuple(extra)
+    key = (kind, t.data_ptr(), t._version, tuple(t.shape), t.stride(), t.dtype, t.device) + tuple(extra)
     hit = _memo_store.get(key)
     if hit is not None:
         _memo_store.move_to_end(key)
@@ -167,8 +167,6 @@ def scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum", return_ar
     if dim < 0 or dim >= src.dim():
         raise IndexError("dim out of range")
     want_arg = return_arg and red in (GNO_MIN, GNO_MAX)
-    if out is not None and red not in (GNO_SUM, GNO_MUL):
-        raise NotImplementedError("gno_b200: out= is supported for sum/mul only")
 
     idx1d = _index_as_1d(index, src, dim)
     if idx1d is None:
@@ -182,8 +180,11 @@ def scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum", return_ar
         N = int(dim_size)
     elif out is not None:
         N = out.size(dim)
+    elif index.numel() == 0:
+        N = 0
     else:
-        N = int(index.max()) + 1 if index.numel() > 0 else 0  # host sync, as upstream
+        # host sync, as upstream — once per index tensor (identity + version), like the plan
+        N = _memo("dim_size", index, (), lambda: int(index.max()) + 1, capacity=16)
 
     src = src.contiguous()
     shape = list(src.shape)
@@ -205,34 +206,48 @@ def scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum", return_ar
 
     if idx1d is not None:
         plan = plan_cache.get(idx1d.contiguous() if not idx1d.is_contiguous() else idx1d, N)
+        # torch_scatter's out= forms: sum/mul accumulate in the kernel; mean = (out + sum) / count;
+        # min/max start from out and keep it (arg = sentinel) unless an element beats it strictly
+        prev = out if (accumulate and red in (GNO_MIN, GNO_MAX)) else None
+        kacc = accumulate and prev is None
+        kred = "sum" if (accumulate and red == GNO_MEAN) else reduce
+        if prev is not None:
+            out = torch.empty(out_shape, dtype=src.dtype, device=src.device)
+        karg = want_arg or prev is not None
         if K == 1 and B > 1:
-            arg2 = _segment_reduce_lastdim(plan, src.view(B, E), reduce, plan.perm, plan.perm,
-                                           out.view(B, N), accumulate, want_arg, E)
-            if want_arg:
+            arg2 = _segment_reduce_lastdim(plan, src.view(B, E), kred, plan.perm, plan.perm,
+                                           out.view(B, N), kacc, karg, E)
+            if karg:
                 arg = arg2.view(out_shape)
         else:
             s3, o3 = src.view(B, E, K), out.view(B, N, K)
             args = []
             for b in range(B):
-                r = segment_reduce(plan, s3[b], reduce, gidx=plan.perm, eid=plan.perm, out=o3[b],
-                                   accumulate=accumulate, want_arg=want_arg, arg_fill=E)
-                if want_arg:
+                r = segment_reduce(plan, s3[b], kred, gidx=plan.perm, eid=plan.perm, out=o3[b],
+                                   accumulate=kacc, want_arg=karg, arg_fill=E)
+                if karg:
                     args.append(r[1])
-            if want_arg:
+            if karg:
                 arg = (args[0] if B == 1 else torch.stack(args)).view(out_shape)
+        if accumulate and red == GNO_MEAN:
+            cnt = (plan.rowptr[1:] - plan.rowptr[:-1]).clamp_(min=1).to(out.dtype)
+            out.div_(cnt.view([1] * dim + [N] + [1] * (len(out_shape) - dim - 1)))
+        if prev is not None:
+            win = (arg != E) & ((out > prev) if red == GNO_MAX else (out < prev))
+            prev.copy_(torch.where(win, out, prev))
+            out = prev
+            arg = torch.where(win, arg, torch.full_like(arg, E)) if want_arg else None
     else:
-        if accumulate:
-            raise NotImplementedError("gno_b200: out= with a full-shape index is not supported")
         index = index.contiguous()
         dt = _dtype_id(src)
         if want_arg:
             arg = torch.empty(out_shape, dtype=torch.int64, device=src.device)
         nbytes = ctypes.c_size_t()
-        check(lib.gno_scatter_elementwise_workspace(B, N, K, dt, red, ctypes.byref(nbytes)))
+        check(lib.gno_scatter_elementwise_workspace(B, E, N, K, dt, red, ctypes.byref(nbytes)))
         ws = _workspace(nbytes.value, src.device) if nbytes.value else None
         with torch.cuda.device(src.device):
             check(lib.gno_scatter_elementwise(_ptr(src), _ptr(index), B, E, K, _ptr(out), _ptr(arg),
-                                              N, dt, red, _ptr(ws), nbytes.value,
+                                              N, dt, red, 1 if accumulate else 0, _ptr(ws), nbytes.value,
                                               _stream(src.device)))
     return (out, arg) if want_arg else out
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GNO_ABI_VERSION 1
+#define GNO_ABI_VERSION 2
 
 typedef void* gno_stream_t; /* a cudaStream_t */
 
@@ -248,15 +248,24 @@ int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes,
  * op_bm_scripts/benchmark_scatter_{add,max,min,mean}.py:60-84 pass: src and
  * index viewed as [B, E, K], out as [B, N, K]:
  *   out[b, index[b,e,k], k] = reduce(src[b,e,k]).
- * Deterministic values for MIN/MAX and deterministic arg (lowest e among
- * ties); SUM/MEAN/MUL accumulate in fp32 in `ws` and round once.
+ * One launch when the N bins of up to 16 adjacent columns fit in shared
+ * memory (every script shape): the input is streamed once, every update is a
+ * shared-memory atomic, no global atomics and no workspace
+ * (gno_scatter_elementwise_workspace then returns 0).  MIN/MAX values and arg
+ * are deterministic (lowest e among ties, like the sequential upstream loop);
+ * fp16 SUM/MEAN accumulate exactly in 64-bit fixed point (order-independent,
+ * one rounding); fp32/bf16 SUM/MEAN and MUL accumulate in fp32 and round once.
+ * Larger N falls back to fp32 L2 atomics in `ws`.
+ *   accumulate  non-zero = torch_scatter's out= form: combine with the values
+ *               already in out (on-chip path only)
  */
-int gno_scatter_elementwise_workspace(int64_t B, int64_t N, int64_t K,
-                                      int dtype, int reduce, size_t* bytes);
+int gno_scatter_elementwise_workspace(int64_t B, int64_t E, int64_t N,
+                                      int64_t K, int dtype, int reduce,
+                                      size_t* bytes);
 int gno_scatter_elementwise(const void* src, const int64_t* index, int64_t B,
                             int64_t E, int64_t K, void* out, int64_t* arg,
-                            int64_t N, int dtype, int reduce, void* ws,
-                            size_t ws_bytes, gno_stream_t stream);
+                            int64_t N, int dtype, int reduce, int accumulate,
+                            void* ws, size_t ws_bytes, gno_stream_t stream);
 
 /* ------------------------------------------------- coalesce / transpose -- */
 /*

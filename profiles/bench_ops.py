@@ -55,12 +55,16 @@ def timeit(fn, iters, flush=False):
     return statistics.median(ts)
 
 
+RESULTS = []  # every emitted line, for callers that run this in-process (bench.py per_config)
+
+
 def emit(name, ms, units, unit_name, abytes, **extra):
     gbs = abytes / (ms * 1e-3) / 1e9
     line = {"op": name, "ms": round(ms, 4), unit_name + "_per_s": units / (ms * 1e-3),
             "algorithmic_GB": round(abytes / 1e9, 3), "achieved_GBps": round(gbs, 1),
             "frac_of_peak": round(gbs / PEAK, 4), "peak_GBps": PEAK, "peak_source": PEAK_SRC}
     line.update(extra)
+    RESULTS.append(line)
     print(json.dumps(line), flush=True)
 
 

@@ -72,6 +72,33 @@ def _worker(rank, world, port, N, E, F, ret):
         recv = aggc.exchange_needed(x[rank::world].contiguous(), gather_rows=lambda t, r: t.index_select(0, r))
         got, _ = oracle.gather_scatter(recv, aggc.src_needed, d_r, hi - lo, "sum")
         ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
+        # K-stage needed-rows exchange pipelined over destination sub-ranges: stage s delivers
+        # exactly the rows sub-range s still misses (stage-major receive layout)
+        for fr in (None, [0.1, 0.3, 0.6]):
+            aggs = DistAggregator(bounds, s_r, d_r, exchange="needed", cyclic_rows=N, stages=3, stage_fracs=fr,
+                                  row_weight=2)
+            recv = aggs.exchange_needed(x[rank::world].contiguous(), gather_rows=lambda t, r: t.index_select(0, r))
+            ok &= recv.size(0) == torch.unique(s_r).numel()
+            sb = aggs.sub_bounds
+            ok &= int(sb[0]) == 0 and int(sb[-1]) == hi - lo
+            got = torch.zeros(hi - lo, F)
+            seen = 0
+            for s in range(3):
+                m = aggs.stage_of_edge == s
+                a, b = int(sb[s]), int(sb[s + 1])
+                ok &= bool(((d_r[m] >= a) & (d_r[m] < b)).all())
+                seen += int(m.sum())
+                if m.any():  # every source of stage s has landed once stages 0..s are delivered
+                    ok &= int(aggs.src_needed[m].max()) < aggs.stage_row0[s + 1]
+                got[a:b] = oracle.gather_scatter(recv, aggs.src_needed[m], d_r[m] - a, b - a, "sum")[0]
+            ok &= seen == s_r.numel()
+            ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
+            # the offsets the owners were told (put_off) are the receivers' own block starts
+            mine = torch.tensor(aggs.recv_off)            # [stage][owner] on this rank
+            allr = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            for q in range(world):
+                ok &= [allr[q][s][rank].item() for s in range(3)] == [aggs.put_off[s][q] for s in range(3)]
         ret[rank] = (bool(ok), int(d_r.numel()))
     finally:
         dist.destroy_process_group()

@@ -70,6 +70,23 @@ def _worker(rank, world, port, ret):
                               cyclic_rows=N)
         got = aggc.aggregate(x[rank::world].contiguous().to(dev), "max", return_arg=True)
         ok &= torch.equal(got[0].cpu(), want[lo:hi])
+        # K-stage exchange pipelined over destination sub-ranges, overlapped with the reduction on a
+        # second stream: peer-store kernel (push) and NCCL all-to-all (needed)
+        wsum, _ = oracle.gather_scatter(x, src, dst, N, "sum")
+        l2g = torch.nonzero((dst >= lo) & (dst < hi)).flatten()
+        for mode, K, fr in (("push", 3, [0.2, 0.3, 0.5]), ("push", 4, None), ("needed", 2, None)):
+            aggs = DistAggregator(bounds, shards[rank][0].to(dev), shards[rank][1].to(dev), exchange=mode,
+                                  cyclic_rows=N, stages=K, stage_fracs=fr, row_weight=4)
+            xl = x[rank::world].contiguous().to(dev)
+            for _ in range(3):
+                got, garg = aggs.aggregate(xl, "max", return_arg=True)
+                ok &= torch.equal(got.cpu(), want[lo:hi])
+                garg = garg.cpu()
+                sent = garg == shards[rank][0].numel()
+                mapped = torch.where(sent, torch.full_like(garg, E), l2g[garg.clamp(max=max(l2g.numel() - 1, 0))])
+                ok &= torch.equal(mapped, warg[lo:hi])
+                got = aggs.aggregate(xl, "sum")
+                ok &= torch.allclose(got.cpu(), wsum[lo:hi], rtol=1e-5, atol=1e-3)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
@@ -83,3 +100,46 @@ def test_partitioned_aggregation_nccl():
         ret = m.dict()
         mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
         assert all(ret[r] for r in range(world)), dict(ret)
+
+
+def _worker_world1(rank, world, port, ret):
+    """The staged exchange on ONE GPU (a 1-rank NCCL group): every code path of the K-stage push /
+    needed pipeline — stage plans, stage-major receive layout, the peer-store kernel writing into
+    this rank's own symmetric buffer, the second stream and its events — without a second device."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    try:
+        from gno_b200.dist import DistAggregator
+        g = torch.Generator().manual_seed(9)
+        N, E, F = 4001, 300_000, 128
+        dst = (torch.rand(E, generator=g) ** 3 * N).long().clamp_(0, N - 1)
+        src = (torch.rand(E, generator=g) ** 2 * N).long().clamp_(0, N - 1)
+        x = ((torch.randn(N, F, generator=g) * 4).round() / 4).to(torch.bfloat16)
+        bounds = torch.tensor([0, N])
+        wsum, _ = oracle.gather_scatter(x.float(), src, dst, N, "sum")
+        wmax, warg = oracle.gather_scatter(x.float(), src, dst, N, "max")
+        ok = True
+        for mode, K, fr in (("push", 4, [0.1, 0.2, 0.3, 0.4]), ("push", 2, None), ("needed", 3, None), ("push", 1, None)):
+            agg = DistAggregator(bounds, src.to(dev), dst.to(dev), rank=0, world=1, exchange=mode, cyclic_rows=N,
+                                 stages=K, stage_fracs=fr, row_weight=4)
+            for _ in range(2):
+                got = agg.aggregate(x.to(dev), "sum")
+                ok &= torch.allclose(got.float().cpu(), wsum, rtol=1e-2, atol=1e-2)
+                gm, ga = agg.aggregate(x.to(dev), "max", return_arg=True)
+                ok &= torch.equal(gm.float().cpu(), wmax)
+                ok &= torch.equal(ga.cpu(), warg)
+        ret[0] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_staged_exchange_single_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker_world1, args=(1, _free_port(), ret), nprocs=1, join=True)
+        assert ret[0]

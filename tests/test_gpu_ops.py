@@ -576,3 +576,117 @@ def test_upstream_published_examples(cuda):
     v = up.SPMM
     out = torch_sparse.spmm(v["index"].to(cuda), v["value"].to(cuda), v["m"], v["n"], v["matrix"].to(cuda))
     assert torch.equal(out.cpu(), v["out"])
+
+
+# ---- full-shape index: the one-launch shared-memory path and its edges --------------------------
+def _ref_minmax_with_out(m, a, out0, E, red):
+    """torch_scatter's out= form for min/max from the oracle's fresh result: out0 is the starting
+    value and survives (arg = E) unless an element beats it strictly."""
+    win = (a != E) & ((m > out0) if red == "max" else (m < out0))
+    return torch.where(win, m, out0), torch.where(win, a, torch.full_like(a, E))
+
+
+@pytest.mark.parametrize("dim", [0, 1])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.bfloat16])
+def test_scatter_full_shape_special_values(cuda, dim, dtype):
+    """NaN / inf / signed zeros / the dtype's finite extremes through the on-chip path: fp16 sums
+    leave the exact fixed-point bins for fp32 ones, extremes never win a max/min, ties keep the
+    first position and the winner keeps its own sign bit."""
+    import gno_b200
+    g = torch.Generator().manual_seed(17)
+    L = 97
+    src = ((torch.rand(L, L, generator=g) * 8).round() / 8 - 0.5).to(dtype)
+    fin = torch.finfo(dtype)
+    specials = torch.tensor([float("nan"), float("inf"), float("-inf"), 0.0, -0.0, fin.max, fin.min], dtype=dtype)
+    pos = torch.randint(0, L * L, (60,), generator=g)
+    src.view(-1)[pos] = specials[torch.randint(0, specials.numel(), (60,), generator=g)]
+    idx = torch.randint(0, 23, (L, L), generator=g)
+    for red in ("sum", "mean", "max", "min"):
+        got = gno_b200.scatter(src.to(cuda), idx.to(cuda), dim, None, 23, red, return_arg=True)
+        want, warg = oracle.scatter(src, idx, dim, 23, red)
+        if red in ("max", "min"):
+            assert torch.equal(got[0].cpu().view(torch.int16 if dtype != torch.float32 else torch.int32),
+                               want.view(torch.int16 if dtype != torch.float32 else torch.int32)), red
+            assert torch.equal(got[1].cpu(), warg), red
+        else:
+            g_, w_ = got.float().cpu(), want.float()
+            assert torch.equal(torch.isnan(g_), torch.isnan(w_)) and torch.equal(torch.isinf(g_), torch.isinf(w_))
+            ok = torch.isfinite(w_)
+            assert torch.equal(torch.sign(g_[~ok & ~torch.isnan(w_)]), torch.sign(w_[~ok & ~torch.isnan(w_)]))
+            fin_src = torch.where(torch.isfinite(src.float()), src.float().abs(), torch.zeros(()))
+            scale = oracle.scatter(fin_src, idx, dim, 23, red)[0]
+            err = (g_ - w_).abs()[ok]
+            assert not (err > TOL[dtype] * torch.maximum(scale, w_.abs())[ok] + 1e-30).any(), red
+
+
+def test_scatter_full_shape_fp16_sum_is_exact(cuda):
+    """fp16 sums accumulate in 64-bit fixed point: the result is the correctly rounded exact sum,
+    whatever the order (checked against an fp64 sum), and repeated calls are bit-identical."""
+    import gno_b200
+    g = torch.Generator().manual_seed(23)
+    L = 512
+    src = (torch.randn(L, L, generator=g) * 30).half()
+    idx = torch.randint(0, 7, (L, L), generator=g)       # ~37k terms per bin: fp32 order would matter
+    for dim in (0, 1):
+        a = gno_b200.scatter(src.to(cuda), idx.to(cuda), dim, None, 7, "sum")
+        b = gno_b200.scatter(src.to(cuda), idx.to(cuda), dim, None, 7, "sum")
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+        exact = torch.zeros(a.shape, dtype=torch.float64).scatter_add_(dim, idx, src.double())
+        assert torch.equal(a.cpu().view(torch.int16), exact.half().view(torch.int16))
+
+
+@pytest.mark.parametrize("shape,dim,N", [((70_000, 3), 0, 11), ((4, 100_000), 1, 60_000), ((3, 500, 20), 1, 40),
+                                         ((2, 3, 70_000), 2, 9)])
+def test_scatter_full_shape_path_selection(cuda, shape, dim, N):
+    """Positions beyond 16 bits (64-bit packed keys), N too large for shared-memory bins (L2-atomic
+    fallback), 3-D inputs: all against the oracle."""
+    import gno_b200
+    g = torch.Generator().manual_seed(sum(shape))
+    src = ((torch.rand(*shape, generator=g) * 64).round() / 64).half()
+    idx = torch.randint(0, N, shape, generator=g)
+    for red in ("sum", "max", "mean", "min", "mul"):
+        s = (src * 0.25 + 0.875) if red == "mul" else src
+        got = gno_b200.scatter(s.to(cuda), idx.to(cuda), dim, None, N, red, return_arg=True)
+        want, warg = oracle.scatter(s, idx, dim, N, red)
+        if red in ("max", "min"):
+            assert torch.equal(got[0].cpu(), want) and torch.equal(got[1].cpu(), warg), red
+        else:
+            scale = oracle.scatter(s.float().abs(), idx, dim, N, red)[0] if red != "mul" else None
+            close(got, want, torch.float16, scale)
+
+
+@pytest.mark.parametrize("full_shape", [True, False])
+def test_scatter_out_forms(cuda, full_shape):
+    """torch_scatter's out= argument for every reduce (upstream scatter.py: sum/mul accumulate,
+    mean = (out + sum) / count, min/max start from out and report arg only where src wins)."""
+    import torch_scatter
+    g = torch.Generator().manual_seed(31)
+    E, F, N = 400, 6, 19
+    src = (torch.rand(E, F, generator=g) * 16).round() / 16
+    idx1 = torch.randint(0, N - 2, (E,), generator=g)           # rows N-2, N-1 stay empty
+    idx = idx1.view(-1, 1).expand(E, F).contiguous() if full_shape else idx1
+    if full_shape:
+        idx = torch.randint(0, N - 2, (E, F), generator=g)
+    out0 = (torch.rand(N, F, generator=g) * 16).round() / 16
+    ix_full = idx if full_shape else idx1.view(-1, 1).expand(E, F)
+    for red in ("sum", "mul", "mean", "max", "min"):
+        s = src * 0.5 + 0.75 if red == "mul" else src
+        fn = getattr(torch_scatter, "scatter_" + red)
+        o = out0.clone().to(cuda)
+        got = fn(s.to(cuda), idx.to(cuda), 0, o)
+        fresh, farg = oracle.scatter(s, ix_full.contiguous(), 0, N, red if red != "mean" else "sum")
+        if red == "sum":
+            want = out0 + fresh
+        elif red == "mul":
+            want = out0 * fresh
+        elif red == "mean":
+            cnt = torch.zeros(N, F).scatter_add_(0, ix_full, torch.ones(E, F)).clamp_(min=1)
+            want = (out0 + fresh) / cnt
+        else:
+            want, warg = _ref_minmax_with_out(fresh, farg, out0, E, red)
+        if red in ("max", "min"):
+            assert got[0].data_ptr() == o.data_ptr()
+            assert torch.equal(got[0].cpu(), want) and torch.equal(got[1].cpu(), warg), red
+        else:
+            assert got.data_ptr() == o.data_ptr()
+            assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-5), red
