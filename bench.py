@@ -466,8 +466,9 @@ def run_rmat(args):
         fracs = [float(v) for v in args.stage_fracs.split(",")] if args.stage_fracs else None
         if fracs is not None and len(fracs) != stages:
             raise SystemExit("--stage-fracs needs one share per stage")
+        own = args.ownership if args.ownership != "auto" else ("xorfold" if world & (world - 1) == 0 else "cyclic")
         kw = dict(rank=rank, world=world, cyclic_rows=N, stages=stages, stage_fracs=fracs,
-                  row_weight=args.row_weight)
+                  row_weight=args.row_weight, split=args.split, ownership=own, push_blocks=args.push_blocks)
         try:
             agg = DistAggregator(bounds, src, dst, exchange=args.exchange, **kw)
             if args.exchange == "push":
@@ -484,7 +485,7 @@ def run_rmat(args):
     else:
         plan = planmod.build_plan(dst, n_out)
         gidx = plan.sorted_ids(src)
-        plans = [(plan, gidx, plan.perm, 0, n_out)]
+        plans = [(plan, gidx, plan.perm, 0, n_out, False)]
         n_needed = n_own = 0
     torch.cuda.synchronize()
     plan_ms = (time.perf_counter() - t0) * 1e3
@@ -522,9 +523,10 @@ def run_rmat(args):
     ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ka.record()
     for _ in range(args.steps):
-        for p, g_, _, r0, r1 in plans:
-            if r1 > r0:
-                gno_b200.segment_reduce(p, x_gather, "sum", gidx=g_, out=out[r0:r1])
+        if world > 1:
+            agg.reduce_stages(x_gather, "sum", out)
+        else:
+            gno_b200.segment_reduce(plan, x_gather, "sum", gidx=gidx, out=out)
     kb.record()
     torch.cuda.synchronize()
     sampler.mark()
@@ -549,9 +551,15 @@ def run_rmat(args):
     step()
     torch.cuda.synchronize()
     if world > 1:
+        from gno_b200.dist import xorfold_global_ids
         x_glob = torch.empty(N, F, dtype=dtype, device=dev)
         for q in range(world):
-            x_glob[q::world] = x_local if q == rank else feature_block(q, world, N, F, dtype, dev)
+            blk = x_local if q == rank else feature_block(q, world, N, F, dtype, dev)
+            if own == "xorfold":
+                x_glob[xorfold_global_ids(q, world, blk.size(0), dev)] = blk
+            else:
+                x_glob[q::world] = blk
+            del blk
     else:
         x_glob = x_local
     t0 = time.perf_counter()
@@ -582,16 +590,17 @@ def run_rmat(args):
             traffic = json.load(f).get(args.workload)
     detail = {"edges_rank0": e_local, "rows_rank0": n_out, "plan_build_ms": plan_ms,
               "max_row_len": max(p.max_len for p, *_ in plans),
-              "empty_rows_rank0": sum(p.n_empty for p, *_ in plans),
+              "empty_rows_rank0": plans[0][0].n_empty if len(plans) == 1 else None,
               "chunk_len": plans[0][0].chunk_len,
               "exchange": args.exchange if world > 1 else None, "stages": stages if world > 1 else None,
-              "stage_rows_rank0": [r1 - r0 for *_, r0, r1 in plans] if world > 1 else None,
+              "split": args.split if world > 1 else None,
+              "stage_edges_rank0": [p.E for p, *_ in plans] if world > 1 else None,
               "stage_recv_rows_rank0": ([agg.stage_row0[s + 1] - agg.stage_row0[s] for s in range(stages)]
                                         if world > 1 else None),
               "exchange_bytes_in_rank0": (n_needed - n_own) * F * es,
               "local_reduce_ms_max_over_ranks": k_ms_max, "exchange_only_ms_max_over_ranks": x_ms_max,
-              "parallelism": (f"edge-balanced dst ranges x{world} (row weight {args.row_weight}), cyclic feature "
-                              f"ownership, needed-rows {args.exchange} exchange in {stages} destination stages "
+              "parallelism": (f"edge-balanced dst ranges x{world} (row weight {args.row_weight}), {own} feature "
+                              f"ownership, needed-rows {args.exchange} exchange in {stages} {args.split} stages "
                               "overlapped with the reduction") if world > 1 else "single GPU"}
 
     # ---- e2e: host buffers through the public API, every step ----
@@ -615,7 +624,8 @@ def run_rmat(args):
         del src, dst, x_local, out
         gno_b200.clear_caches()
         torch.cuda.empty_cache()
-        e2e = run_e2e_rmat(world, rank, dev, dist, bounds, x_host, ei_host, out_host, N, E)
+        e2e = run_e2e_rmat(world, rank, dev, dist, bounds, x_host, ei_host, out_host, N, E,
+                           own if world > 1 else "cyclic")
         del x_host, ei_host, out_host
     except Exception as ex:  # e.g. the box cannot pin 3 x 17 GB: keep the device-resident numbers
         e2e = {"value": None, "unit": "edges/s", "error": repr(ex)[:300]}
@@ -649,7 +659,7 @@ def run_rmat(args):
         dist.destroy_process_group()
 
 
-def run_e2e_rmat(world, rank, dev, dist, bounds, x_host, ei_host, out_host, N, E):
+def run_e2e_rmat(world, rank, dev, dist, bounds, x_host, ei_host, out_host, N, E, own):
     """Host-buffer path: every step copies that step's inputs (x shard and the int64 edge shard)
     from pinned host memory, builds the plan (N>1: the whole partitioned aggregator — request
     lists, NCCL needed-rows exchange), aggregates, and copies the result to pinned host memory."""
@@ -673,7 +683,7 @@ def run_e2e_rmat(world, rank, dev, dist, bounds, x_host, ei_host, out_host, N, E
             xd = x_host.to(dev, non_blocking=True)
             eid = ei_host.to(dev, non_blocking=True)
             a2 = DistAggregator(bounds, eid[0], eid[1], rank=rank, world=world, cyclic_rows=N,
-                                exchange="needed")
+                                exchange="needed", ownership=own)
             o = a2.aggregate(xd, "sum")
             out_host.copy_(o, non_blocking=True)
             torch.cuda.synchronize()
@@ -968,7 +978,18 @@ def main():
                     help="exchange pipeline depth at N>1 (rmat: destination sub-ranges, default 4; products: "
                          "row chunks of the all-gather, default 4 at N>=4)")
     ap.add_argument("--stage-fracs", default="",
-                    help="rmat workloads: comma-separated cost shares of the destination stages (default equal)")
+                    help="rmat workloads: comma-separated shares of the stages (dest split: cost share of each "
+                         "destination sub-range; source split: share of the remote rows in each remote stage)")
+    ap.add_argument("--split", default="source", choices=["source", "dest"],
+                    help="rmat workloads at N>1: pipeline the exchange over groups of SOURCE rows (own rows, "
+                         "then remote rows by decreasing reference count; stages accumulate) or over "
+                         "DESTINATION sub-ranges (every row written once)")
+    ap.add_argument("--ownership", default="auto", choices=["auto", "cyclic", "xorfold"],
+                    help="rmat workloads at N>1: feature row i lives on rank i %% N (cyclic) or on the XOR of "
+                         "the log2(N)-bit groups of i (xorfold: balanced on R-MAT ids, whose bits are skewed); "
+                         "auto = xorfold for power-of-two N")
+    ap.add_argument("--push-blocks", type=int, default=296,
+                    help="grid cap of the push kernel when it runs beside the reduction (0 = fill the chip)")
     ap.add_argument("--per-config", type=int, default=1,
                     help="N=1: also time the other BASELINE.json configs' kernels (per_config object)")
     args = ap.parse_args()

@@ -49,9 +49,9 @@ __global__ void gather_i64_kernel(const int64_t* __restrict__ src, const uint32_
 
 template <bool FAST>
 __global__ void head_kernel(const void* __restrict__ skeys, const int64_t* __restrict__ scol,
-                            int32_t* __restrict__ head, int64_t E) {
+                            int32_t* __restrict__ head, int64_t E, int keep_all) {
   GNO_GS(k, E) {
-    bool h = (k == 0);
+    bool h = (k == 0) || keep_all;  // keep_all: sort only, duplicates stay separate entries
     if (!h) {
       if (FAST) {
         const uint32_t* r = static_cast<const uint32_t*>(skeys);
@@ -217,6 +217,7 @@ int gno_coalesce(const int64_t* row, const int64_t* col, const void* value, int6
   GNO_CHECK_ARG(m > 0 && n > 0, "gno_coalesce: empty shape with E > 0");
   GNO_CHECK_ARG(value == nullptr || (out_value != nullptr && K > 0), "gno_coalesce: value without out_value/K");
   const bool fast = (flags & 1) != 0;
+  const int keep_all = (flags & 2) ? 1 : 0;
   if (fast) {
     GNO_CHECK_ARG(m <= (int64_t(1) << 32), "gno_coalesce: fast path needs m <= 2^32");
   } else {
@@ -237,7 +238,7 @@ int gno_coalesce(const int64_t* row, const int64_t* col, const void* value, int6
     if (rc) return rc;
     gather_i64_kernel<<<cgrid(E), 256, 0, s>>>(col, c.perm, c.scol, E);
     GNO_LAUNCHED("gather_i64_kernel");
-    head_kernel<true><<<cgrid(E), 256, 0, s>>>(c.skeys, c.scol, c.head, E);
+    head_kernel<true><<<cgrid(E), 256, 0, s>>>(c.skeys, c.scol, c.head, E, keep_all);
   } else {
     make_keys64_kernel<<<cgrid(E), 256, 0, s>>>(row, col, (uint64_t*)c.keys, E, n);
     GNO_LAUNCHED("make_keys64_kernel");
@@ -245,7 +246,7 @@ int gno_coalesce(const int64_t* row, const int64_t* col, const void* value, int6
     rc = sort_pairs(c.keys, c.skeys, nullptr, c.perm, E, 8, 4, 0, bits_for_u64(maxkey), c.sort_ws,
                     c.sort_bytes, s);
     if (rc) return rc;
-    head_kernel<false><<<cgrid(E), 256, 0, s>>>(c.skeys, nullptr, c.head, E);
+    head_kernel<false><<<cgrid(E), 256, 0, s>>>(c.skeys, nullptr, c.head, E, keep_all);
   }
   GNO_LAUNCHED("head_kernel");
   rc = exclusive_scan_i32(c.head, c.pos, E, c.scan_ws, s);

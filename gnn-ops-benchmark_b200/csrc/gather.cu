@@ -1,6 +1,7 @@
 // Row gather (index_select along dim 0) and the last-dim segment reduce
 // (index_select / index_add_ along dim 1 of a [B, L] matrix).
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -87,21 +88,49 @@ struct PushParams {
   int P;
 };
 
+// Posted peer stores need no round trip, so a few resident warps per SM keep NVLink busy as long
+// as each thread has several row loads in flight (kPushUnroll).  The grid is therefore small by
+// choice when the exchange shares the GPU with the reduction (max_blocks): a push kernel that is
+// allowed to fill every SM slot at high priority starves the reduction for the whole transfer
+// and the two serialise (measured: RMAT-26 at P=2, 25.0 ms sequential vs 26.1 ms "overlapped").
+constexpr int kPushUnroll = 4;
+
+template <typename V>
+__device__ __forceinline__ void push_locate(const PushParams& p, int64_t i, int64_t vpr, const V*& src,
+                                            V*& dst) {
+  const int64_t s0 = i / vpr, j = i - s0 * vpr;
+  int64_t s = s0 + p.start;
+  if (s >= p.n_serve) s -= p.n_serve;
+  int q = 0;
+#pragma unroll 1
+  while (q + 1 < p.P && s >= p.seg[q + 1]) ++q;
+  const int64_t r = p.serve_rows ? p.serve_rows[s] : (s - p.seg[q]);  // NULL: every peer gets all rows
+  src = reinterpret_cast<const V*>(p.x + r * p.src_stride) + j;
+  dst = reinterpret_cast<V*>(p.peer_buf[q] + (p.row_off[q] + (s - p.seg[q])) * p.dst_stride) + j;
+}
+
 template <typename V>
 __global__ void __launch_bounds__(256) push_rows_kernel(const PushParams p) {
   const int64_t vpr = p.row_bytes / (int64_t)sizeof(V);
   const int64_t total = p.n_serve * vpr;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t s0 = i / vpr, j = i - s0 * vpr;
-    int64_t s = s0 + p.start;
-    if (s >= p.n_serve) s -= p.n_serve;
-    int q = 0;
-#pragma unroll 1
-    while (q + 1 < p.P && s >= p.seg[q + 1]) ++q;
-    const int64_t r = p.serve_rows ? p.serve_rows[s] : (s - p.seg[q]);  // NULL: every peer gets all rows
-    const V v = __ldg(reinterpret_cast<const V*>(p.x + r * p.src_stride) + j);
-    reinterpret_cast<V*>(p.peer_buf[q] + (p.row_off[q] + (s - p.seg[q])) * p.dst_stride)[j] = v;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (kPushUnroll - 1) * stride < total; i += kPushUnroll * stride) {
+    const V* src[kPushUnroll];
+    V* dst[kPushUnroll];
+    V v[kPushUnroll];
+#pragma unroll
+    for (int u = 0; u < kPushUnroll; ++u) push_locate<V>(p, i + u * stride, vpr, src[u], dst[u]);
+#pragma unroll
+    for (int u = 0; u < kPushUnroll; ++u) v[u] = __ldg(src[u]);
+#pragma unroll
+    for (int u = 0; u < kPushUnroll; ++u) *dst[u] = v[u];
+  }
+  for (; i < total; i += stride) {
+    const V* src;
+    V* dst;
+    push_locate<V>(p, i, vpr, src, dst);
+    *dst = __ldg(src);
   }
 }
 
@@ -223,7 +252,7 @@ int gno_pad_rows(const void* src, int64_t rows, int64_t row_bytes, int64_t src_s
 int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes, const int64_t* serve_rows,
                   int64_t n_serve, int n_peers, void* const* peer_bufs, const int64_t* seg,
                   const int64_t* row_off, int64_t dst_stride_bytes, int64_t start_slot,
-                  gno_stream_t stream) {
+                  int max_blocks, gno_stream_t stream) {
   if (n_serve == 0 || row_bytes == 0) return GNO_OK;
   GNO_CHECK_ARG(x && peer_bufs && seg && row_off && n_serve > 0 && row_bytes > 0,
                 "gno_push_rows: bad argument");
@@ -249,10 +278,19 @@ int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes, co
   p.seg[n_peers] = seg[n_peers];
   GNO_CHECK_ARG(seg[0] == 0 && seg[n_peers] == n_serve, "gno_push_rows: seg must cover [0, n_serve)");
   cudaStream_t s = (cudaStream_t)stream;
-  auto grid = [](int64_t n) {
+  const int64_t cap = max_blocks > 0 ? (int64_t)max_blocks : (int64_t)kNumSMs * 32;
+  auto grid = [cap](int64_t n) {
     int64_t b = ceil_div(n, 256);
-    return (unsigned)(b > (int64_t)kNumSMs * 32 ? (int64_t)kNumSMs * 32 : b);
+    return (unsigned)(b > cap ? cap : b);
   };
+  // Kernels that prefer different L1 / shared-memory splits cannot share an SM; give the push
+  // kernel the split of the reduction it runs beside (GNO_PUSH_CARVEOUT = percent of shared memory).
+  static const int carve = getenv("GNO_PUSH_CARVEOUT") ? atoi(getenv("GNO_PUSH_CARVEOUT")) : -1;
+  static bool carve_set = false;
+  if (carve >= 0 && !carve_set) {
+    GNO_CUDA(cudaFuncSetAttribute(push_rows_kernel<uint4>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    carve_set = true;
+  }
   if (a % 16 == 0) {
     push_rows_kernel<uint4><<<grid(n_serve * (row_bytes / 16)), 256, 0, s>>>(p);
   } else if (a % 4 == 0) {

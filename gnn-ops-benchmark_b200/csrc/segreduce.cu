@@ -196,10 +196,11 @@ __device__ __forceinline__ float finalize(float a, int e, float prev, bool mean,
 // two to a register and are compared with one HSET2 per pair (the fp32 form cost five
 // instructions per element — unpack, compare, two selects — and made the bf16 max+arg kernel
 // issue-bound at 0.83 of the HBM roofline).
-template <typename T, int VB, int RED>
+template <typename T, int VB, int RED, bool HAS_W = false>
 struct Accum {
   static constexpr int EPV = VB / (int)sizeof(T);
-  static constexpr bool kPacked = sizeof(T) == 2 && EPV >= 2 && (RED == GNO_MIN || RED == GNO_MAX);
+  // (weighted extremes compare products, which are formed in fp32: no packed form)
+  static constexpr bool kPacked = sizeof(T) == 2 && EPV >= 2 && (RED == GNO_MIN || RED == GNO_MAX) && !HAS_W;
   float f[kPacked ? 1 : EPV];
   uint32_t h[kPacked ? EPV / 2 : 1];
 
@@ -309,11 +310,11 @@ __device__ __forceinline__ void flush_row(const SegParams& p, int row, int chunk
 
 // acc (+= | *= | min | max)= one gathered vector
 template <typename T, int VB, int RED, bool ARG, bool HAS_W>
-__device__ __forceinline__ void accumulate(Accum<T, VB, RED>& acc,
+__device__ __forceinline__ void accumulate(Accum<T, VB, RED, HAS_W>& acc,
                                            int (&ae)[ARG ? VB / (int)sizeof(T) : 1],
                                            const Words<VB>& val, int e, float w) {
   constexpr int EPV = VB / (int)sizeof(T);
-  if constexpr (Accum<T, VB, RED>::kPacked) {
+  if constexpr (Accum<T, VB, RED, HAS_W>::kPacked) {
 #pragma unroll
     for (int j = 0; j < EPV / 2; ++j) {
       if constexpr (ARG) {
@@ -333,8 +334,11 @@ __device__ __forceinline__ void accumulate(Accum<T, VB, RED>& acc,
       } else if constexpr (RED == GNO_MUL) {
         acc.f[i] *= f;
       } else {
-        if (better<RED>(f, acc.f[i])) {
-          acc.f[i] = f;
+        // torch_sparse spmm_min/max with edge values compares value * mat, rounded to the
+        // storage type like upstream's scalar_t product
+        const float c = HAS_W ? bits_to_f<T>(f_to_bits<T>(w * f) & (sizeof(T) == 2 ? 0xffffu : 0xffffffffu)) : f;
+        if (better<RED>(c, acc.f[i])) {
+          acc.f[i] = c;
           if constexpr (ARG) ae[i] = e;
         }
       }
@@ -343,11 +347,11 @@ __device__ __forceinline__ void accumulate(Accum<T, VB, RED>& acc,
 }
 
 // flush_row on an Accum (unpacks the packed 16-bit extremes; row boundaries are rare next to edges)
-template <typename T, int VB, int RED, bool ARG>
+template <typename T, int VB, int RED, bool ARG, typename ACC>
 __device__ __forceinline__ void flush_acc(const SegParams& p, int row, int chunk, bool head, bool tail,
-                                          int seg_len, int v, const Accum<T, VB, RED>& acc,
+                                          int seg_len, int v, const ACC& acc,
                                           const int (&ae)[ARG ? VB / (int)sizeof(T) : 1]) {
-  if constexpr (Accum<T, VB, RED>::kPacked) {
+  if constexpr (ACC::kPacked) {
     float f[VB / (int)sizeof(T)];
     acc.unpack(f);
     flush_row<T, VB, RED, ARG>(p, row, chunk, head, tail, seg_len, v, f, ae);
@@ -384,7 +388,7 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
   const int32_t* eid = p.eid ? p.eid + k0 : nullptr;
   const T* wgt = HAS_W ? static_cast<const T*>(p.w) + k0 : nullptr;
 
-  Accum<T, VB, RED> acc;
+  Accum<T, VB, RED, HAS_W> acc;
   int ae[ARG ? EPV : 1];
   acc.reset();
   if constexpr (ARG) {
@@ -620,7 +624,7 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
   const bool has_idx = p.gidx != nullptr;
   const bool e_is_k = ARG && !sep_e && !(p.eid && p.eid == p.gidx);  // eid == NULL: edge id = k
 
-  Accum<T, VB, RED> acc;
+  Accum<T, VB, RED, HAS_W> acc;
   int ae[ARG ? EPV : 1];
   acc.reset();
   if constexpr (ARG) {
@@ -855,6 +859,11 @@ static int launch_seg(const SegParams& p, cudaStream_t s) {
   const int64_t workers = p.n_chunks * p.ncoltiles;
   const int64_t warps = ceil_div(workers, 32 / p.G);
   const int64_t blocks = ceil_div(warps, kSegWarps);
+  static const int carve = getenv("GNO_SEG_CARVEOUT") ? atoi(getenv("GNO_SEG_CARVEOUT")) : -1;
+  if (carve >= 0) {
+    GNO_CUDA(cudaFuncSetAttribute(segreduce_staged_kernel<T, VB, RED, ARG, HAS_W, U>,
+                                  cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  }
   if (blocks > 0 && p.staged) {
     const size_t smem = 128 + (size_t)seg_staged_bytes(p, (int)sizeof(T), ARG, HAS_W);
     segreduce_staged_kernel<T, VB, RED, ARG, HAS_W, U><<<(unsigned)blocks, kSegThreads, smem, s>>>(p);
@@ -888,9 +897,9 @@ static int dispatch_red(const SegParams& p, int reduce, bool /*with_arg*/, bool 
     // that ties between +0.0 and -0.0 resolve to the first occurrence, which
     // keeps the VALUES bit-identical to the sequential upstream loop.
     case GNO_MIN:
-      return launch_seg<T, VB, GNO_MIN, true, false>(p, s);
+      return has_w ? launch_seg<T, VB, GNO_MIN, true, true>(p, s) : launch_seg<T, VB, GNO_MIN, true, false>(p, s);
     case GNO_MAX:
-      return launch_seg<T, VB, GNO_MAX, true, false>(p, s);
+      return has_w ? launch_seg<T, VB, GNO_MAX, true, true>(p, s) : launch_seg<T, VB, GNO_MAX, true, false>(p, s);
   }
   return fail(GNO_ERR_INVALID, "gno_segment_reduce: unknown reduce %d", reduce);
 }
@@ -957,8 +966,8 @@ int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows, int64_t 
                 "gno_segment_reduce: arg output only for MIN/MAX");
   GNO_CHECK_ARG(!accumulate || reduce == GNO_SUM || reduce == GNO_MUL,
                 "gno_segment_reduce: accumulate only for SUM/MUL");
-  if (w != nullptr && !(reduce == GNO_SUM || reduce == GNO_MEAN))
-    return fail(GNO_ERR_UNSUPPORTED, "gno_segment_reduce: edge weights only with SUM/MEAN");
+  if (w != nullptr && reduce == GNO_MUL)
+    return fail(GNO_ERR_UNSUPPORTED, "gno_segment_reduce: edge weights with MUL are not defined upstream");
 
   const int es = dtype_size(dtype);
   GNO_CHECK_ARG((((uintptr_t)x | (uintptr_t)out) % es) == 0,

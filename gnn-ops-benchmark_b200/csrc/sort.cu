@@ -55,14 +55,46 @@ struct ScatterSmem {
   ValT ex_v[HAS_VAL ? kSortSub : 1];
 };
 
-template <typename KeyT, typename ValT, bool HAS_VAL>
+// Lanes of the warp that hold the same NBITS-bit digit as this lane: one ballot per digit bit.
+// Per bit: VOTE, SEL, LOP3 (ptxas moves the digit bits into predicates with one R2P per key): three
+// issue slots; the C++ form (shift, and, compare, ballot, select, not, and) cost eight
+// (profiles/r1n_sort_scatter_source_lines.txt).
+template <int B>
+__device__ __forceinline__ void match_step(unsigned& peers, unsigned d) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 v, t, m;\n\t"
+      "and.b32 t, %1, %2;\n\t"
+      "setp.ne.u32 p, t, 0;\n\t"
+      "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+      "selp.b32 m, 0, 0xffffffff, p;\n\t"
+      "lop3.b32 %0, %0, v, m, 0x60;\n\t}"   // peers & (v ^ m): v for a set bit, ~v for a clear one
+      : "+r"(peers)
+      : "r"(d), "n"(1u << B));
+}
+template <int NBITS>
+__device__ __forceinline__ unsigned match_digit(unsigned d) {
+  unsigned peers = 0xffffffffu;
+  match_step<0>(peers, d);
+  if constexpr (NBITS > 1) match_step<1>(peers, d);
+  if constexpr (NBITS > 2) match_step<2>(peers, d);
+  if constexpr (NBITS > 3) match_step<3>(peers, d);
+  if constexpr (NBITS > 4) match_step<4>(peers, d);
+  if constexpr (NBITS > 5) match_step<5>(peers, d);
+  if constexpr (NBITS > 6) match_step<6>(peers, d);
+  if constexpr (NBITS > 7) match_step<7>(peers, d);
+  return peers;
+}
+
+template <typename KeyT, typename ValT, bool HAS_VAL, int NBITS>
 __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 4 : 3)
     radix_scatter_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                          const ValT* __restrict__ vals_in, ValT* __restrict__ vals_out,
                          const int32_t* __restrict__ offsets, int64_t n, int shift, unsigned mask,
-                         int nbits, int subtiles, int64_t num_tiles) {
+                         int subtiles, int64_t num_tiles) {
+  // NBITS = ballots per key: the digit (key >> shift) & mask has at most NBITS bits
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScatterSmem<KeyT, ValT, HAS_VAL>& sm = *reinterpret_cast<ScatterSmem<KeyT, ValT, HAS_VAL>*>(smem_raw);
+  constexpr int kGroup = 4;  // rounds whose ballots are issued together (ILP across the RMW chain)
 
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
   const unsigned lt_mask = (1u << l) - 1u;
@@ -72,6 +104,7 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 4 : 3)
   for (int sub = 0; sub < subtiles; ++sub) {
     const int64_t base = (tile * subtiles + sub) * (int64_t)kSortSub;
     if (base >= n) break;
+    const bool full = base + kSortSub <= n;
 #pragma unroll
     for (int i = 0; i < kSortWarps; ++i) sm.warp_hist[i][t] = 0;
     __syncthreads();
@@ -79,35 +112,39 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 4 : 3)
     KeyT key[kSortItems];
     int pos[kSortItems];
     const int64_t wbase = base + (int64_t)w * (kSortItems * 32) + l;
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < kSortItems; ++i) {
-      const int64_t idx = wbase + i * 32;
-      key[i] = (idx < n) ? keys_in[idx] : ~KeyT(0);
+      for (int i = 0; i < kSortItems; ++i) key[i] = keys_in[wbase + i * 32];
+    } else {
+#pragma unroll
+      for (int i = 0; i < kSortItems; ++i) {
+        const int64_t idx = wbase + i * 32;
+        key[i] = (idx < n) ? keys_in[idx] : ~KeyT(0);
+      }
     }
     // Warp-level ranking: equal digits in one round get consecutive ranks in
     // lane order; rounds are ordered, so ranks follow input order.
+    int* hist = sm.warp_hist[w];
 #pragma unroll
-    for (int i = 0; i < kSortItems; ++i) {
-      const unsigned d = (unsigned)(key[i] >> shift) & mask;
-      // lanes holding the same digit: one ballot per digit bit (MATCH.ANY measured slower on
-      // sm_100a); passes are split evenly, so most digits are narrower than 8 bits
-      unsigned peers = 0xffffffffu;
+    for (int i0 = 0; i0 < kSortItems; i0 += kGroup) {
+      unsigned dg[kGroup], peers[kGroup];
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        if (b < nbits) {
-          const unsigned vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
-          peers &= ((d >> b) & 1u) ? vote : ~vote;
+      for (int g = 0; g < kGroup; ++g) {
+        dg[g] = (unsigned)(key[i0 + g] >> shift) & mask;
+        peers[g] = match_digit<NBITS>(dg[g]);
+      }
+#pragma unroll
+      for (int g = 0; g < kGroup; ++g) {
+        const int leader = __ffs(peers[g]) - 1;
+        int old = 0;
+        if (l == leader) {
+          old = hist[dg[g]];
+          hist[dg[g]] = old + __popc(peers[g]);
         }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        pos[i0 + g] = old + __popc(peers[g] & lt_mask);
+        __syncwarp();
       }
-      const int leader = __ffs(peers) - 1;
-      int old = 0;
-      if (l == leader) {
-        old = sm.warp_hist[w][d];
-        sm.warp_hist[w][d] = old + __popc(peers);
-      }
-      old = __shfl_sync(0xffffffffu, old, leader);
-      pos[i] = old + __popc(peers & lt_mask);
-      __syncwarp();
     }
     __syncthreads();
     // Thread t owns digit t: exclusive scan over warps, then over digits.
@@ -127,33 +164,52 @@ __global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 4 : 3)
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
       const unsigned d = (unsigned)(key[i] >> shift) & mask;
-      pos[i] += sm.digit_start[d] + sm.warp_hist[w][d];
+      pos[i] += sm.digit_start[d] + hist[d];
       sm.ex_k[pos[i]] = key[i];
     }
     if (HAS_VAL) {  // payload goes straight from global to its sorted slot
+      if (vals_in != nullptr && full) {
+        ValT v[kSortItems];
 #pragma unroll
-      for (int i = 0; i < kSortItems; ++i) {
-        const int64_t idx = wbase + i * 32;
-        ValT v;
-        if (vals_in != nullptr)
-          v = (idx < n) ? vals_in[idx] : ValT(0);
-        else
-          v = (ValT)idx;  // identity payload: first pass of an argsort
-        sm.ex_v[pos[i]] = v;
+        for (int i = 0; i < kSortItems; ++i) v[i] = vals_in[wbase + i * 32];
+#pragma unroll
+        for (int i = 0; i < kSortItems; ++i) sm.ex_v[pos[i]] = v[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < kSortItems; ++i) {
+          const int64_t idx = wbase + i * 32;
+          ValT v;
+          if (vals_in != nullptr)
+            v = (idx < n) ? vals_in[idx] : ValT(0);
+          else
+            v = (ValT)idx;  // identity payload: first pass of an argsort
+          sm.ex_v[pos[i]] = v;
+        }
       }
     }
     __syncthreads();
-    const int64_t remain = n - base;
-    const int valid = remain < kSortSub ? (int)remain : kSortSub;
+    if (full) {
 #pragma unroll
-    for (int j = 0; j < kSortItems; ++j) {
-      const int p = j * kSortThreads + t;
-      if (p < valid) {
+      for (int j = 0; j < kSortItems; ++j) {
+        const int p = j * kSortThreads + t;
         const KeyT k = sm.ex_k[p];
         const unsigned d = (unsigned)(k >> shift) & mask;
         const int gpos = sm.gbase[d] + p;
         keys_out[gpos] = k;
         if (HAS_VAL) vals_out[gpos] = sm.ex_v[p];
+      }
+    } else {
+      const int valid = (int)(n - base);
+#pragma unroll
+      for (int j = 0; j < kSortItems; ++j) {
+        const int p = j * kSortThreads + t;
+        if (p < valid) {
+          const KeyT k = sm.ex_k[p];
+          const unsigned d = (unsigned)(k >> shift) & mask;
+          const int gpos = sm.gbase[d] + p;
+          keys_out[gpos] = k;
+          if (HAS_VAL) vals_out[gpos] = sm.ex_v[p];
+        }
       }
     }
     __syncthreads();
@@ -212,7 +268,13 @@ static int sort_impl(const KeyT* keys_in, KeyT* keys_out, const ValT* vals_in, V
   const int passes = (end_bit - begin_bit + 7) / 8;
   const size_t smem_bytes = sizeof(ScatterSmem<KeyT, ValT, HAS_VAL>);
   if (smem_bytes > 48 * 1024) {
-    GNO_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ValT, HAS_VAL>,
+    GNO_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ValT, HAS_VAL, 5>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    GNO_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ValT, HAS_VAL, 6>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    GNO_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ValT, HAS_VAL, 7>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    GNO_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ValT, HAS_VAL, 8>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   }
   if (passes == 0) {
@@ -246,8 +308,14 @@ static int sort_impl(const KeyT* keys_in, KeyT* keys_out, const ValT* vals_in, V
     GNO_LAUNCHED("radix_hist_kernel");
     int rc = exclusive_scan_i32(counts, counts, (int64_t)kRadix * g.num_tiles, scan_ws, s);
     if (rc) return rc;
-    radix_scatter_kernel<KeyT, ValT, HAS_VAL><<<(unsigned)g.num_tiles, kSortThreads, smem_bytes, s>>>(
-        src_k, dst_k, src_v, dst_v, counts, n, shift, mask, nb, g.subtiles, g.num_tiles);
+#define GNO_SCATTER(NB)                                                                          \
+  radix_scatter_kernel<KeyT, ValT, HAS_VAL, NB><<<(unsigned)g.num_tiles, kSortThreads, smem_bytes, s>>>( \
+      src_k, dst_k, src_v, dst_v, counts, n, shift, mask, g.subtiles, g.num_tiles)
+    if (nb <= 5) GNO_SCATTER(5);
+    else if (nb == 6) GNO_SCATTER(6);
+    else if (nb == 7) GNO_SCATTER(7);
+    else GNO_SCATTER(8);
+#undef GNO_SCATTER
     GNO_LAUNCHED("radix_scatter_kernel");
     src_k = dst_k;
     src_v = dst_v;

@@ -50,6 +50,34 @@ def stage_ranges(row_costs, stages, fracs=None):
     return torch.cummax(bounds, 0).values
 
 
+def xorfold_owner(ids, world):
+    """Row ownership for power-of-two world sizes: owner = XOR of all log2(world)-bit groups of the
+    id, local row = id >> log2(world).  A bijection like cyclic ownership (owner = id % world), but
+    balanced on graphs whose id BITS are skewed: every bit of an R-MAT id is 1 with probability
+    b + d = 0.24, so under cyclic ownership rank 0 of 2 owns 76 % of the referenced rows."""
+    p = world.bit_length() - 1
+    if world < 1 or (1 << p) != world:
+        raise ValueError("ownership='xorfold' needs a power-of-two world size")
+    if p == 0:
+        return torch.zeros_like(ids), ids.clone()
+    fold = torch.zeros_like(ids)
+    t = ids.clone()
+    while bool((t != 0).any()) if ids.numel() else False:
+        fold ^= t & (world - 1)
+        t = t >> p
+    return fold, ids >> p
+
+
+def xorfold_global_ids(owner, world, n_local, device=None):
+    """Global ids of the rows `owner` holds under xorfold ownership, in local-row order."""
+    p = world.bit_length() - 1
+    j = torch.arange(n_local, dtype=torch.int64, device=device)
+    if p == 0:
+        return j
+    fold_hi, _ = xorfold_owner(j << p, world)     # fold of the id with its low bits zeroed
+    return (j << p) | (fold_hi ^ owner)
+
+
 def partition_graph(src, dst, num_nodes, world):
     """Split a global edge list into per-rank shards by destination range.
 
@@ -79,7 +107,7 @@ class DistAggregator:
 
     def __init__(self, bounds, src_global, dst_local, rank=None, world=None, group=None, stages=1,
                  feature_bounds=None, exchange="allgather", cyclic_rows=None, stage_fracs=None,
-                 row_weight=0):
+                 row_weight=0, split="dest", ownership="cyclic", push_blocks=296):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -95,10 +123,18 @@ class DistAggregator:
             # of a skewed graph over all owners, so the needed-rows exchange is balanced on the
             # SENDING side too (with contiguous blocks the owner of the low ids serves every rank).
             n_rows = int(cyclic_rows)
-            self.n_local = (n_rows - self.rank + self.world - 1) // self.world
-            self.max_rows = (n_rows + self.world - 1) // self.world
-            owner = src_global % self.world
-            local = torch.div(src_global, self.world, rounding_mode="floor")
+            if ownership == "xorfold":
+                owner, local = xorfold_owner(src_global, self.world)
+                if n_rows % self.world:
+                    raise ValueError("ownership='xorfold' needs a row count divisible by the world size")
+                self.n_local = self.max_rows = n_rows // self.world
+            elif ownership == "cyclic":
+                self.n_local = (n_rows - self.rank + self.world - 1) // self.world
+                self.max_rows = (n_rows + self.world - 1) // self.world
+                owner = src_global % self.world
+                local = torch.div(src_global, self.world, rounding_mode="floor")
+            else:
+                raise ValueError("ownership must be 'cyclic' or 'xorfold'")
         else:
             rows = self.xbounds[1:] - self.xbounds[:-1]
             self.n_local = int(rows[self.rank])
@@ -111,6 +147,9 @@ class DistAggregator:
             # needed-rows exchanges pipeline over DESTINATION sub-ranges (see _setup_needed)
             self.xstages, stages = max(1, int(stages)), 1
             self.stage_fracs, self.row_weight = stage_fracs, int(row_weight)
+            if split not in ("dest", "source"):
+                raise ValueError("split must be 'dest' or 'source'")
+            self.split = split if self.xstages > 1 else "dest"
         self.stages = max(1, min(int(stages), max(self.max_rows, 1)))
         # single-stage layout: row of the padded gather buffer [P * max_rows, F]
         self.src_padded = owner * self.max_rows + local if exchange in ("allgather", "allgather_push") else None
@@ -129,6 +168,9 @@ class DistAggregator:
         self._stage_plans = None
         self._push_stream = None
         self._push_events = None
+        self._row_counts = None
+        self.push_blocks = int(push_blocks)
+        self.trace = None   # set to [] to collect (label, cuda event) pairs of one staged step
         self.exchange_mode = exchange
         if exchange in ("needed", "push"):
             self._setup_needed(src_global, owner, local)
@@ -146,12 +188,22 @@ class DistAggregator:
         owners gather those rows and deliver them in the order of the receiver's gather buffer, so
         the gather index of an edge is just the position of its source in that buffer.
 
-        K > 1 stages: this rank's destination rows are cut into K contiguous sub-ranges (stage s
-        reduces sub-range s); a needed source row belongs to the FIRST stage whose edges read it,
-        and the receive buffer is laid out stage-major, owner-minor.  Stage s of the exchange then
-        delivers exactly the rows stage s of the reduction is still missing, so the reduction of
-        sub-range s can run while the rows of s+1 are in flight — without splitting any output row
-        (every row is written once, by one stage: no accumulate pass, no extra rounding)."""
+        K > 1 stages, split="dest": this rank's destination rows are cut into K contiguous
+        sub-ranges (stage s reduces sub-range s); a needed source row belongs to the FIRST stage
+        whose edges read it, and the receive buffer is laid out stage-major, owner-minor.  Stage s of
+        the exchange then delivers exactly the rows stage s of the reduction is still missing, so
+        the reduction of sub-range s can run while the rows of s+1 are in flight — without
+        splitting any output row (every row is written once, by one stage; works for every reduce).
+
+        K > 1 stages, split="source" (sum / mean): the needed SOURCE rows are cut into K groups —
+        stage 0 = the rows this rank owns itself (nothing to wait for), stages 1..K-1 = the remote
+        rows in order of decreasing reference count (stage_fracs = the share of the remote rows in
+        each).  Stage s reduces the edges whose source lies in group s, accumulating into the
+        output.  On a skewed graph the first remote group is small in bytes but covers most of the
+        edges, so almost all of the exchange hides behind the reduction (the destination split
+        cannot avoid that every sub-range needs the hub rows first: measured on RMAT-26 at P=2,
+        10 % of the edges already read 42 % of the needed rows).  Cost: each stage re-reads and
+        re-writes the output rows it touches, and the 16-bit output is rounded once per stage."""
         P, K = self.world, self.xstages
         dev = src_global.device
         key = owner * self.max_rows + local                      # ascending key = grouped by owner
@@ -159,7 +211,22 @@ class DistAggregator:
         uowner = torch.div(uniq, self.max_rows, rounding_mode="floor")
         req = uniq - uowner * self.max_rows                        # row inside the owner's shard
         n_u = int(uniq.numel())
-        if K > 1:
+        if K > 1 and self.split == "source":
+            fr = self.stage_fracs if self.stage_fracs is not None else [1.0 / (K - 1)] * (K - 1)
+            if len(fr) != K - 1 or min(fr) < 0 or sum(fr) <= 0:
+                raise ValueError("split='source': stage_fracs holds one share per REMOTE stage (stages - 1)")
+            refs = torch.bincount(inv, minlength=n_u)
+            remote = torch.nonzero(uowner != self.rank).flatten()
+            by_refs = remote[torch.argsort(refs[remote], descending=True, stable=True)]
+            cum = torch.cumsum(torch.tensor(fr, dtype=torch.float64), 0) / sum(fr)
+            cuts = [0] + [int(round(float(c) * by_refs.numel())) for c in cum]
+            cuts[-1] = by_refs.numel()
+            first = torch.zeros(n_u, dtype=torch.int64, device=dev)
+            for s_ in range(1, K):
+                first[by_refs[cuts[s_ - 1]:cuts[s_]]] = s_
+            self.sub_bounds = None
+            self.stage_of_edge = first[inv]
+        elif K > 1:
             counts = torch.bincount(self.dst_local, minlength=self.n_out) + self.row_weight
             self.sub_bounds = stage_ranges(counts, K, self.stage_fracs).cpu()
             sb = self.sub_bounds.to(dev)
@@ -272,9 +339,10 @@ class DistAggregator:
             st = self._push_bufs[key] = (t, hdl, ptrs, stages)
         return st
 
-    def _push_stage(self, x_local, st, s):
+    def _push_stage(self, x_local, st, s, max_blocks=0):
         """Launch stage s of the exchange on the current stream: one kernel that reads every row a
-        peer needs for its stage s once from local HBM and stores it into that peer's buffer."""
+        peer needs for its stage s once from local HBM and stores it into that peer's buffer.
+        max_blocks caps its grid when it runs beside the reduction (0 = fill the chip)."""
         from ._lib import check, lib
         from .plan import _ptr, _stream
         t, hdl, ptrs, stages = st
@@ -284,7 +352,8 @@ class DistAggregator:
         with torch.cuda.device(x_local.device):
             check(lib.gno_push_rows(_ptr(x_local), F * es, x_local.stride(0) * es, _ptr(rows),
                                     rows.numel(), self.world, ptrs, seg_c, off_c, F * es,
-                                    seg[(self.rank + 1) % self.world], _stream(x_local.device)))
+                                    seg[(self.rank + 1) % self.world], int(max_blocks),
+                                    _stream(x_local.device)))
 
     def exchange_push(self, x_local):
         """All stages back to back on the current stream (no overlap); returns the receive buffer."""
@@ -326,7 +395,7 @@ class DistAggregator:
         with torch.cuda.device(x_local.device):
             check(lib.gno_push_rows(_ptr(x_local), F * es, x_local.stride(0) * es, None,
                                     self.world * self.n_local, self.world, ptrs, seg, off, F * es,
-                                    ((self.rank + 1) % self.world) * self.n_local,
+                                    ((self.rank + 1) % self.world) * self.n_local, 0,
                                     _stream(x_local.device)))
         hdl.barrier(channel=1)
         return t
@@ -389,37 +458,70 @@ class DistAggregator:
         return self._stage_plans
 
     def xstage_plans(self):
-        """needed / push exchange with K destination stages: one plan per destination sub-range
-        [(plan, gidx, eid, row_lo, row_hi)]; eid maps a sorted edge of the sub-range back to its
-        position in this rank's edge list (the arg outputs)."""
+        """needed / push exchange with K stages: one plan per stage
+        [(plan, gidx, eid, row_lo, row_hi, accumulate)].  split="dest": the plan of destination
+        sub-range [row_lo, row_hi); split="source": a plan over all rows holding the edges whose
+        source lies in group s, accumulated onto the earlier stages.  eid maps a sorted edge back
+        to its position in this rank's edge list (the arg outputs)."""
         if self._stage_plans is None:
             from . import plan as planmod
             self._stage_plans = []
             for s in range(self.xstages):
-                lo, hi = int(self.sub_bounds[s]), int(self.sub_bounds[s + 1])
                 if self.xstages == 1:
                     p, gidx = self.plan()
-                    self._stage_plans.append((p, gidx, p.perm, lo, hi))
+                    self._stage_plans.append((p, gidx, p.perm, 0, self.n_out, False))
                     continue
                 where = torch.nonzero(self.stage_of_edge == s).flatten()
+                if self.split == "source":
+                    lo, hi, acc = 0, self.n_out, s > 0
+                else:
+                    lo, hi, acc = int(self.sub_bounds[s]), int(self.sub_bounds[s + 1]), False
                 p = planmod.build_plan(self.dst_local[where] - lo, hi - lo)
                 gidx = p.sorted_ids(self.src_needed[where])
                 eid = p.sorted_ids(where)
-                self._stage_plans.append((p, gidx, eid, lo, hi))
+                self._stage_plans.append((p, gidx, eid, lo, hi, acc))
         return self._stage_plans
+
+    def reduce_stages(self, recv, reduce, out, want_arg=False, arg=None, events=None):
+        """The local half of a staged step: every stage plan over the receive buffer (waiting for
+        events[s] first when given).  Also what bench.py times as the kernel-only loop."""
+        from . import ops
+        cur = torch.cuda.current_stream(recv.device)
+        for s, (p, gidx, eid, lo, hi, acc) in enumerate(self.xstage_plans()):
+            if events is not None:
+                cur.wait_event(events[s])
+            self._mark(f"reduce{s} start", cur)
+            if hi == lo or (acc and p.E_valid == 0):
+                continue
+            r = ops.segment_reduce(p, recv, reduce, gidx=gidx, eid=eid, want_arg=want_arg,
+                                   arg_fill=self.dst_local.numel(), out=out[lo:hi], accumulate=acc)
+            if want_arg:
+                arg[lo:hi].copy_(r[1])
+            self._mark(f"reduce{s} end", cur)
+
+    def _mark(self, label, stream):
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            self.trace.append((label, e))
 
     def _aggregate_staged(self, x_local, reduce, want_arg, x_full, out):
         """K-stage needed-rows exchange overlapped with the reduction (exchange = push | needed).
 
-        Stage s of the exchange delivers the rows destination sub-range s still misses; the
-        reduction of sub-range s runs as soon as they have landed, while stage s+1 is in flight.
+        Stage s of the exchange delivers the rows stage s of the reduction still misses; the
+        reduction of stage s runs as soon as they have landed, while stage s+1 is in flight.
         The exchange runs on a second, high-priority stream so its CTAs take SM slots as
         reduction CTAs retire instead of queueing behind the whole launch."""
-        from . import ops
         dev = x_local.device
         F = x_local.size(1)
-        plans = self.xstage_plans()
+        self.xstage_plans()
         x_local = x_local.contiguous()
+        kred = reduce
+        if self.split == "source":
+            if reduce not in ("sum", "mean") or want_arg:
+                raise NotImplementedError("split='source' accumulates across stages: sum / mean only "
+                                          "(use split='dest' for min / max / mul)")
+            kred = "sum"
         if out is None:
             out = torch.empty((self.n_out, F), dtype=x_local.dtype, device=dev)
         arg = torch.empty((self.n_out, F), dtype=torch.int64, device=dev) if want_arg else None
@@ -436,24 +538,29 @@ class DistAggregator:
             recv, hdl = st[0][:self.n_needed], st[1]
         else:
             recv = x_full if x_full is not None else torch.empty((self.n_needed, F), dtype=x_local.dtype, device=dev)
+        # split="source": stage 0 holds only rows this rank owns (a local copy into its own
+        # buffer): nothing crosses NVLink, so no cross-rank barrier has to follow it
+        local0 = self.split == "source"
+        self._mark("step start", cur)
         with torch.cuda.stream(ps):
             if push:
                 hdl.barrier(channel=0)      # every peer is done reading its buffer from the previous call
+                self._mark("barrier0 done", ps)
             for s in range(self.xstages):
                 if push:
-                    self._push_stage(x_local, st, s)
-                    hdl.barrier(channel=1)  # stage s has landed everywhere
+                    self._push_stage(x_local, st, s, self.push_blocks)
+                    self._mark(f"push{s} done", ps)
+                    if not (local0 and s == 0):
+                        hdl.barrier(channel=1)  # stage s has landed everywhere
+                        self._mark(f"barrier after push{s} done", ps)
                 else:
                     self.exchange_needed(x_local, recv, stage=s)
                 ev[s].record(ps)
-        for s, (p, gidx, eid, lo, hi) in enumerate(plans):
-            cur.wait_event(ev[s])
-            if hi == lo:
-                continue
-            r = ops.segment_reduce(p, recv, reduce, gidx=gidx, eid=eid, want_arg=want_arg,
-                                   arg_fill=self.dst_local.numel(), out=out[lo:hi])
-            if want_arg:
-                arg[lo:hi].copy_(r[1])
+        self.reduce_stages(recv, kred, out, want_arg, arg, events=ev)
+        if reduce == "mean" and self.split == "source":
+            if self._row_counts is None:
+                self._row_counts = torch.bincount(self.dst_local, minlength=self.n_out).clamp_(min=1)
+            out.div_(self._row_counts.to(out.dtype).view(-1, 1))
         return (out, arg) if want_arg else out
 
     def aggregate(self, x_local, reduce="sum", return_arg=False, x_full=None, out=None, stage_bufs=None):

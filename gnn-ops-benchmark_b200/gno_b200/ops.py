@@ -44,7 +44,7 @@ def _reduce_id(reduce):
 _memo_store = collections.OrderedDict()
 
 
-def _memo(kind, t, extra, builder, capacity=8):
+def _memo(kind, t, extra, builder, capacity=32):
     """Small LRU keyed on a tensor's identity/version (keeps the tensor alive)."""
     key = (kind, t.data_ptr(), t._version, tuple(t.shape), t.stride(), t.dtype, t.device) + tuple(extra)
     hit = _memo_store.get(key)
@@ -293,6 +293,8 @@ def index_add(input, dim, index, source, inplace=False):
 def index_select(input, dim, index):
     """torch.index_select on 2-D tensors (dim 0: vectorised row gather; dim 1: last-dim gather)."""
     _need_cuda(input, index)
+    if index.dtype != torch.int64 or index.dim() != 1:
+        raise ValueError("index must be a 1-D int64 tensor")
     if dim < 0:
         dim += input.dim()
     input = input.contiguous()
@@ -317,29 +319,152 @@ def index_select(input, dim, index):
 
 
 # ----------------------------------------------------------------- segment_csr --
+def _csr_plan(indptr, n_elems):
+    """Plan of a 1-D indptr over a dim of n_elems elements, plus the element range it covers.
+    Upstream lets indptr cover a sub-range [indptr[0], indptr[-1]) of the dim and ignores the
+    rest; the plan is built over that range (one host read of the two end pointers per indptr
+    tensor — memoised on its identity like every plan)."""
+    def build():
+        lo, hi = (int(v) for v in indptr[[0, -1]].tolist())
+        if lo < 0 or hi < lo or hi > n_elems:
+            raise ValueError(f"indptr covers [{lo}, {hi}) but the segment dim has {n_elems} elements")
+        ptr = indptr.to(torch.int64)
+        if lo:
+            ptr = ptr - lo
+        return plan_from_rowptr(ptr, hi - lo), lo, hi
+    return _memo("csr_plan", indptr, (int(n_elems),), build)
+
+
+def _csr_nd(src, indptr):
+    """Normalise an N-D indptr (torch_scatter: its leading dims broadcast against src, segments run
+    along dim = indptr.dim() - 1).  Returns (src3 [B, E, K] contiguous, ptr2 [B or 1, M+1], dim)."""
+    dim = indptr.dim() - 1
+    if dim >= src.dim():
+        raise ValueError("indptr has more dims than src")
+    for d in range(dim):
+        if indptr.size(d) not in (1, src.size(d)):
+            raise ValueError("indptr is not broadcastable to src")
+    B = 1
+    for s_ in src.shape[:dim]:
+        B *= s_
+    E = src.size(dim)
+    shared = all(indptr.size(d) == 1 for d in range(dim))
+    if shared:
+        ptr2 = indptr.reshape(1, -1)
+    else:
+        ptr2 = indptr.expand(list(src.shape[:dim]) + [indptr.size(-1)]).reshape(B, -1)
+    return src.contiguous().view(B, E, -1), ptr2, dim
+
+
+def _flat_rowptr(ptr2, B, E):
+    """Per-batch pointers [B, M+1] as ONE rowptr over the flattened [B*E] elements — valid when every
+    batch covers its whole dim (ptr[b, 0] == 0, ptr[b, M] == E).  Returns None otherwise."""
+    def build():
+        ends = ptr2[:, [0, -1]]
+        if not bool(((ends[:, 0] == 0) & (ends[:, 1] == E)).all()):
+            return (None,)
+        off = torch.arange(B, device=ptr2.device, dtype=torch.int64).view(-1, 1) * E
+        flat = torch.cat([(ptr2[:, :-1].to(torch.int64) + off).reshape(-1),
+                          torch.full((1,), B * E, dtype=torch.int64, device=ptr2.device)])
+        return (flat.contiguous(),)
+    return _memo("flat_rowptr", ptr2, (B, E), build)[0]
+
+
+def _segment_ids(ptr2, B, E):
+    """Generic per-batch pointers: the segment of every element as a COO index into [B*M]
+    (elements outside their batch's pointer range get B*M and are dropped by the plan)."""
+    M = ptr2.size(1) - 1
+    e = torch.arange(E, device=ptr2.device, dtype=torch.int64).view(1, -1).expand(B, E).contiguous()
+    p = ptr2.to(torch.int64).contiguous()
+    seg = torch.searchsorted(p, e, right=True) - 1
+    ok = (e >= p[:, :1]) & (e < p[:, -1:])
+    seg = seg + torch.arange(B, device=ptr2.device, dtype=torch.int64).view(-1, 1) * M
+    return torch.where(ok, seg, torch.full_like(seg, B * M)).reshape(-1)
+
+
 def segment_csr(src, indptr, out=None, reduce="sum", return_arg=False):
-    """torch_scatter.segment_csr for 1-D indptr over dim 0 of src."""
-    _need_cuda(src, indptr)
-    if indptr.dim() != 1:
-        raise NotImplementedError("gno_b200.segment_csr covers 1-D indptr")
+    """torch_scatter.segment_csr: segments [indptr[..., m], indptr[..., m+1]) along
+    dim = indptr.dim() - 1 of src; the leading dims of indptr broadcast against src
+    (upstream docstring: src [10, 6, 64], indptr [1, 4] -> out [10, 3, 64])."""
+    _need_cuda(src, indptr, out)
     red = _reduce_id(reduce)
     want_arg = return_arg and red in (GNO_MIN, GNO_MAX)
-    E = src.size(0)
-    plan = _memo("rowptr_plan", indptr, (E,), lambda: plan_from_rowptr(indptr, E))
-    x2 = src.contiguous().view(E, -1)
-    r = segment_reduce(plan, x2, reduce, want_arg=want_arg, arg_fill=E)
-    shape = [plan.N] + list(src.shape[1:])
+    if indptr.dim() < 1 or indptr.size(-1) < 1:
+        raise ValueError("indptr needs at least one pointer along its last dim")
+    if out is not None:
+        raise NotImplementedError("gno_b200.segment_csr: out= is not supported")
+    if indptr.dim() == 1:
+        E = src.size(0)
+        plan, lo, hi = _csr_plan(indptr, E)
+        x2 = src.contiguous().view(E, -1)[lo:hi]
+        r = segment_reduce(plan, x2, reduce, want_arg=want_arg, arg_fill=E)
+        shape = [plan.N] + list(src.shape[1:])
+        if want_arg:
+            arg = r[1]
+            if lo:  # positions are along the whole dim, the sentinel stays src.size(dim)
+                arg = torch.where(arg == E, arg, arg + lo)
+            return r[0].view(shape), arg.view(shape)
+        return r.view(shape)
+    src3, ptr2, dim = _csr_nd(src, indptr)
+    B, E, K = src3.shape
+    M = ptr2.size(1) - 1
+    out_shape = list(src.shape[:dim]) + [M] + list(src.shape[dim + 1:])
+    if ptr2.size(0) == 1 and B > 1:
+        # one pointer row for every batch: move the segment dim first ([E, B*K] rows), reduce with the
+        # 1-D kernel, move back
+        xt = src3.permute(1, 0, 2).reshape(E, B * K)
+        r = segment_csr(xt, ptr2[0], None, reduce, return_arg=want_arg)
+        if want_arg:
+            return (r[0].view(M, B, K).permute(1, 0, 2).reshape(out_shape),
+                    r[1].view(M, B, K).permute(1, 0, 2).reshape(out_shape))
+        return r.view(M, B, K).permute(1, 0, 2).reshape(out_shape)
+    flat = _flat_rowptr(ptr2, B, E) if B > 0 else None
+    x2 = src3.view(B * E, K)
+    if flat is not None:
+        plan = _memo("rowptr_plan", flat, (B * E,), lambda: plan_from_rowptr(flat, B * E))
+        r = segment_reduce(plan, x2, reduce, want_arg=want_arg, arg_fill=B * E)
+    else:
+        ids = _memo("segment_ids", ptr2, (B, E), lambda: _segment_ids(ptr2, B, E))
+        plan = plan_cache.get(ids, B * M)
+        r = segment_reduce(plan, x2, reduce, gidx=plan.perm, eid=plan.perm, want_arg=want_arg,
+                           arg_fill=B * E)
     if want_arg:
-        return r[0].view(shape), r[1].view(shape)
-    return r.view(shape)
+        val, arg = r
+        # flat positions b*E + e -> e along the dim; sentinel -> E
+        arg = torch.where(arg == B * E, torch.full_like(arg, E), arg % max(E, 1))
+        return val.view(out_shape), arg.view(out_shape)
+    return r.view(out_shape)
 
 
 def gather_csr(src, indptr):
-    """torch_scatter.gather_csr: out[k] = src[row(k)] for 1-D indptr."""
+    """torch_scatter.gather_csr: out[..., e, :] = src[..., m, :] for e in segment m, along
+    dim = indptr.dim() - 1; the output has indptr[..., -1] elements along that dim."""
     _need_cuda(src, indptr)
-    counts = indptr[1:] - indptr[:-1]
-    rows = torch.repeat_interleave(torch.arange(counts.numel(), device=src.device), counts)
-    return index_select(src.contiguous().view(src.size(0), -1), 0, rows).view([rows.numel()] + list(src.shape[1:]))
+    if indptr.dim() == 1:
+        M = indptr.numel() - 1
+        if src.size(0) != M:
+            raise ValueError("src must have indptr.numel() - 1 rows")
+        total = _memo("ptr_last", indptr, (), lambda: int(indptr[-1]))
+        plan, lo, hi = _csr_plan(indptr, total)
+        rows = _memo("erow64", plan.rowptr, (), lambda: plan.erow.to(torch.int64))
+        body = index_select(src.contiguous().view(M, -1), 0, rows)
+        if lo:  # elements before the first pointer belong to no segment: zeros, as upstream's empty init
+            body = torch.cat([body.new_zeros((lo, body.size(1))), body])
+        return body.view([total] + list(src.shape[1:]))
+    src3, ptr2, dim = _csr_nd(src, indptr)
+    B, M, K = src3.shape
+    if ptr2.size(1) - 1 != M:
+        raise ValueError("src must have indptr.size(-1) - 1 elements along the segment dim")
+    total = _memo("ptr_last_max", indptr, (), lambda: int(indptr[..., -1].max()))
+    if ptr2.size(0) == 1:
+        r = gather_csr(src3.permute(1, 0, 2).reshape(M, B * K), ptr2[0])
+        return r.view(total, B, K).permute(1, 0, 2).reshape(list(src.shape[:dim]) + [total] + list(src.shape[dim + 1:]))
+    ids = _memo("segment_ids", ptr2, (B, total), lambda: _segment_ids(ptr2, B, total))
+    valid = ids < B * M
+    rows = torch.where(valid, ids, torch.zeros_like(ids))
+    body = index_select(src3.reshape(B * M, K), 0, rows)
+    body = torch.where(valid.view(-1, 1), body, torch.zeros_like(body))
+    return body.view(list(src.shape[:dim]) + [total] + list(src.shape[dim + 1:]))
 
 
 def segment_coo(src, index, out=None, dim_size=None, reduce="sum", return_arg=False):
@@ -413,7 +538,9 @@ def spmm_csr(rowptr, col, value, matrix, reduce="sum", return_arg=False):
     red = _reduce_id(reduce)
     want_arg = return_arg and red in (GNO_MIN, GNO_MAX)
     nnz = col.numel()
-    plan = _memo("rowptr_plan", rowptr, (nnz,), lambda: plan_from_rowptr(rowptr, nnz))
+    plan, lo, hi = _csr_plan(rowptr, nnz)
+    if lo != 0 or hi != nnz:
+        raise ValueError(f"rowptr covers [{lo}, {hi}) but col has {nnz} entries")
 
     def _narrow():
         o = torch.empty(nnz, dtype=torch.int32, device=col.device)
@@ -425,6 +552,34 @@ def spmm_csr(rowptr, col, value, matrix, reduce="sum", return_arg=False):
     w = None if value is None else value.to(matrix.dtype).contiguous()
     return segment_reduce(plan, matrix.contiguous(), reduce, gidx=gidx, weights=w,
                           want_arg=want_arg, arg_fill=nnz)
+
+
+def csr_rows(rowptr, nnz):
+    """Row id of every CSR entry (int64 [nnz]); memoised with the rowptr's plan."""
+    plan, lo, hi = _csr_plan(rowptr, nnz)
+    return _memo("erow64", plan.rowptr, (), lambda: plan.erow.to(torch.int64))
+
+
+def spmm_csr_t(rowptr, col, value, grad, n_cols):
+    """Transposed CSR product  out[c, :] = sum_{k: col[k] = c} value[k] * grad[row[k], :]  — the
+    backward of spmm_csr w.r.t. the dense matrix.  Same segment-reduce kernel; the plan (sorted by
+    column id) is cached on `col`, like upstream caches csr2csc."""
+    _need_cuda(rowptr, col, value, grad)
+    row = csr_rows(rowptr, col.numel())
+    plan = plan_cache.get(col, n_cols)
+    gidx = plan.sorted_ids(row)
+    w = None
+    if value is not None:
+        v = value.detach().to(grad.dtype).contiguous()
+
+        def _permute():
+            o = torch.empty_like(v)
+            with torch.cuda.device(v.device):
+                check(lib.gno_permute_rows(_ptr(v), _ptr(plan.perm), _ptr(o), v.numel(),
+                                           v.element_size(), _stream(v.device)))
+            return o
+        w = _memo("perm_val", value, (plan.rowptr.data_ptr(), str(grad.dtype)), _permute)
+    return segment_reduce(plan, grad.contiguous(), "sum", gidx=gidx, weights=w)
 
 
 # ------------------------------------------------------- coalesce / transpose --
@@ -477,6 +632,18 @@ def coalesce(index, value, m, n, op="add"):
     if inv == 0 and dup == 0:
         return index, value  # upstream early exit: already sorted and unique
     return _coalesce_impl(index[0], index[1], value, m, n, op, 0)
+
+
+def sort_coo(index, value, m, n):
+    """Entries of a COO matrix in (row, col) order, duplicates kept — what torch_sparse's
+    SparseStorage does on construction (storage.py: argsort of row*n+col, no merge)."""
+    _need_cuda(index, value)
+    if index.size(1) <= 1:
+        return index, value
+    inv, _ = coo_order(index, n)
+    if inv == 0:
+        return index, value
+    return _coalesce_impl(index[0], index[1], value, m, n, "add", 2)
 
 
 def transpose(index, value, m, n, coalesced=True):

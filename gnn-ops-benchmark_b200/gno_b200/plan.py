@@ -61,6 +61,12 @@ class CSRPlan:
 
     def sorted_ids(self, ids):
         """int32 copy of `ids` (int64 [E]) reordered by the plan: ids[perm]. Cached."""
+        if ids.dtype != torch.int64 or ids.dim() != 1 or ids.numel() != self.E:
+            raise ValueError(f"ids must be a 1-D int64 tensor of {self.E} elements "
+                             f"(got {ids.dtype}, shape {tuple(ids.shape)})")
+        if ids.device != self.device:
+            raise ValueError("ids must live on the plan's device")
+        ids = ids.contiguous()  # a strided view (a row of edges.t()) is copied, not misread
         key = (ids.data_ptr(), ids._version, ids.numel())
         hit = self._gidx_cache.get(key)
         if hit is not None:
@@ -147,6 +153,9 @@ class PlanCache:
         self.misses = 0
 
     def get(self, index, num_rows, chunk_len=None):
+        if index.dtype != torch.int64 or index.dim() != 1:
+            raise ValueError("plan index must be a 1-D int64 tensor")
+        index = index.contiguous()  # two views of one buffer (t[:E], t[::2]) must not share a plan
         key = (index.data_ptr(), index._version, index.numel(), int(num_rows), chunk_len,
                str(index.device))
         p = self._d.get(key)

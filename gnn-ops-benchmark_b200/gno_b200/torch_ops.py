@@ -48,10 +48,12 @@ def _scatter_impl(reduce, differentiable):
     return fn
 
 
-def _segment_impl(reduce):
+def _segment_impl(reduce, differentiable=False):
     def fn(src, indptr, optional_out):
         if optional_out is not None:
             raise NotImplementedError("gno_b200 segment_csr: out= is not supported")
+        if differentiable and indptr.dim() == 1:
+            return _ag.segment_csr(src, indptr, reduce)
         return _ops.segment_csr(src, indptr, None, reduce, return_arg=reduce in ("min", "max"))
     return fn
 
@@ -66,15 +68,23 @@ def _spmm_sum(opt_row, rowptr, col, opt_value, opt_colptr, opt_csr2csc, mat):
     return _ops.spmm_csr(rowptr, col, opt_value, mat, "sum")
 
 
+def _spmm_sum_ag(opt_row, rowptr, col, opt_value, opt_colptr, opt_csr2csc, mat):
+    return _ag.spmm_csr(rowptr, col, opt_value, mat, "sum")
+
+
 def _spmm_mean(opt_row, rowptr, col, opt_value, opt_rowcount, opt_colptr, opt_csr2csc, mat):
     return _ops.spmm_csr(rowptr, col, opt_value, mat, "mean")
 
 
-def _spmm_minmax(reduce):
+def _spmm_mean_ag(opt_row, rowptr, col, opt_value, opt_rowcount, opt_colptr, opt_csr2csc, mat):
+    return _ag.spmm_csr(rowptr, col, opt_value, mat, "mean")
+
+
+def _spmm_minmax(reduce, differentiable=False):
     def fn(rowptr, col, opt_value, mat):
-        if opt_value is not None:
-            raise NotImplementedError("gno_b200 spmm_min/max: edge values are not supported")
-        return _ops.spmm_csr(rowptr, col, None, mat, reduce, return_arg=True)
+        if differentiable:
+            return _ag.spmm_csr(rowptr, col, opt_value, mat, reduce)
+        return _ops.spmm_csr(rowptr, col, opt_value, mat, reduce, return_arg=True)
     return fn
 
 
@@ -112,12 +122,13 @@ def register():
         for red in ("sum", "mul", "mean", "min", "max"):
             impls["scatter_" + red] = (_scatter_impl(red, False), _scatter_impl(red, True))
         for red in ("sum", "mean", "min", "max"):
-            impls[f"segment_{red}_csr"] = (_segment_impl(red), None)
+            impls[f"segment_{red}_csr"] = (_segment_impl(red), _segment_impl(red, True))
         impls["gather_csr"] = (_gather_csr, None)
         registered["torch_scatter"] = _register("torch_scatter", _SCATTER_SCHEMAS, impls)
     if not registered["torch_sparse"]:
-        impls = {"spmm_sum": (_spmm_sum, None), "spmm_mean": (_spmm_mean, None),
-                 "spmm_min": (_spmm_minmax("min"), None), "spmm_max": (_spmm_minmax("max"), None),
+        impls = {"spmm_sum": (_spmm_sum, _spmm_sum_ag), "spmm_mean": (_spmm_mean, _spmm_mean_ag),
+                 "spmm_min": (_spmm_minmax("min"), _spmm_minmax("min", True)),
+                 "spmm_max": (_spmm_minmax("max"), _spmm_minmax("max", True)),
                  "ind2ptr": (_ind2ptr, None), "ptr2ind": (_ptr2ind, None)}
         registered["torch_sparse"] = _register("torch_sparse", _SPARSE_SCHEMAS, impls)
     return registered

@@ -84,9 +84,12 @@ def scatter(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
 
 def segment_csr(src: torch.Tensor, indptr: torch.Tensor, out: Optional[torch.Tensor] = None,
                 reduce: str = "sum") -> torch.Tensor:
-    if out is not None:
-        raise NotImplementedError("gno_b200 segment_csr: out= is not supported")
-    return _ops.segment_csr(src, indptr, None, reduce)
+    if reduce not in ("sum", "add", "mean", "min", "max"):
+        raise ValueError
+    if out is None and src.requires_grad and torch.is_grad_enabled():
+        r = _ag.segment_csr(src, indptr, "sum" if reduce == "add" else reduce)
+        return r[0] if reduce in ("min", "max") else r
+    return _ops.segment_csr(src, indptr, out, reduce)
 
 
 def segment_sum_csr(src, indptr, out=None):
@@ -102,10 +105,14 @@ def segment_mean_csr(src, indptr, out=None):
 
 
 def segment_min_csr(src, indptr, out=None):
+    if src.requires_grad and torch.is_grad_enabled():
+        return _ag.segment_csr(src, indptr, "min")
     return _ops.segment_csr(src, indptr, None, "min", return_arg=True)
 
 
 def segment_max_csr(src, indptr, out=None):
+    if src.requires_grad and torch.is_grad_enabled():
+        return _ag.segment_csr(src, indptr, "max")
     return _ops.segment_csr(src, indptr, None, "max", return_arg=True)
 
 

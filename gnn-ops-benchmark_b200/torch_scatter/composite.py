@@ -4,7 +4,26 @@ from typing import Optional
 
 import torch
 
+from gno_b200 import autograd as _ag
 from gno_b200 import ops as _ops
+
+
+def _needs_grad(t):
+    return t.requires_grad and torch.is_grad_enabled()
+
+
+def _sc(src, index, dim, dim_size, reduce):
+    """One scatter of the composite: through the autograd Function when src needs a gradient
+    (upstream's composites are differentiable), straight to the kernel otherwise."""
+    if _needs_grad(src):
+        return _ag.scatter(src, index, dim, dim_size, reduce)
+    return _ops.scatter(src, index, dim, None, dim_size, reduce)
+
+
+def _group_max(src, index, dim, dim_size):
+    """Per-group maximum used as the shift of softmax / logsumexp.  The shift cancels in the
+    result, so it is a constant for autograd (no gradient flows through it)."""
+    return _ops.scatter(src.detach(), index, dim, None, dim_size, "max")
 
 
 def _expand(t, index, src, dim):
@@ -25,10 +44,10 @@ def scatter_logsumexp(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
         dim += src.dim()
     if dim_size is None:
         dim_size = int(index.max()) + 1 if index.numel() else 0
-    mx = _ops.scatter(src, index, dim, None, dim_size, "max")
-    rec = (src - _expand(mx, index, src, dim)).exp_()
-    s = _ops.scatter(rec, index, dim, None, dim_size, "sum")
-    return s.add_(eps).log_().add_(mx)
+    mx = _group_max(src, index, dim, dim_size)
+    rec = (src - _expand(mx, index, src, dim)).exp()
+    s = _sc(rec, index, dim, dim_size, "sum")
+    return (s + eps).log() + mx
 
 
 def scatter_softmax(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
@@ -39,9 +58,11 @@ def scatter_softmax(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
         dim += src.dim()
     if dim_size is None:
         dim_size = int(index.max()) + 1 if index.numel() else 0
-    mx = _ops.scatter(src, index, dim, None, dim_size, "max")
-    rec = (src - _expand(mx, index, src, dim)).exp_()
-    s = _ops.scatter(rec, index, dim, None, dim_size, "sum")
+    mx = _group_max(src, index, dim, dim_size)
+    rec = (src - _expand(mx, index, src, dim)).exp()
+    s = _sc(rec, index, dim, dim_size, "sum")
+    if _needs_grad(src):
+        return rec / _expand(s, index, src, dim)
     return rec.div_(_expand(s, index, src, dim))
 
 
@@ -53,10 +74,10 @@ def scatter_log_softmax(src: torch.Tensor, index: torch.Tensor, dim: int = -1, e
         dim += src.dim()
     if dim_size is None:
         dim_size = int(index.max()) + 1 if index.numel() else 0
-    mx = _ops.scatter(src, index, dim, None, dim_size, "max")
+    mx = _group_max(src, index, dim, dim_size)
     rec = src - _expand(mx, index, src, dim)
-    s = _ops.scatter(rec.exp(), index, dim, None, dim_size, "sum")
-    return rec.sub_(_expand(s.add_(eps).log_(), index, src, dim))
+    s = _sc(rec.exp(), index, dim, dim_size, "sum")
+    return rec - _expand((s + eps).log(), index, src, dim)
 
 
 def scatter_std(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
@@ -68,11 +89,11 @@ def scatter_std(src: torch.Tensor, index: torch.Tensor, dim: int = -1,
         dim += src.dim()
     if dim_size is None:
         dim_size = int(index.max()) + 1 if index.numel() else 0
-    ones = torch.ones_like(src)
+    ones = torch.ones_like(src, requires_grad=False)
     count = _ops.scatter(ones, index, dim, None, dim_size, "sum")
-    mean = _ops.scatter(src, index, dim, None, dim_size, "sum") / count.clamp(min=1)
+    mean = _sc(src, index, dim, dim_size, "sum") / count.clamp(min=1)
     var = src - _expand(mean, index, src, dim)
-    var = _ops.scatter(var * var, index, dim, None, dim_size, "sum")
+    var = _sc(var * var, index, dim, dim_size, "sum")
     if unbiased:
         count = count.sub(1).clamp_(min=1)
-    return var.div_(count.add(1e-6)).sqrt_()
+    return (var / (count + 1e-6)).sqrt()

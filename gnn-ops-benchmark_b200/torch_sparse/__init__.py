@@ -29,6 +29,18 @@ def transpose(index: torch.Tensor, value: Optional[torch.Tensor], m: int, n: int
 
 def spmm(index: torch.Tensor, value: torch.Tensor, m: int, n: int,
          matrix: torch.Tensor) -> torch.Tensor:
+    if torch.is_grad_enabled() and (matrix.requires_grad or (value is not None and value.requires_grad)):
+        # differentiable form: the CSR of the row-sorted entries through the autograd Function
+        # (the value permutation is a differentiable indexing op)
+        from gno_b200 import autograd as _ag
+        from gno_b200.plan import plan_cache
+        plan = plan_cache.get(index[0].contiguous(), m)
+        perm = plan.perm.to(torch.int64)
+        col_s = index[1][perm]
+        val_s = value[perm] if value is not None else None
+        squeeze = matrix.dim() == 1
+        out = _ag.spmm_csr(plan.rowptr, col_s, val_s, matrix.unsqueeze(-1) if squeeze else matrix, "sum")
+        return out.squeeze(-1) if squeeze else out
     return _ops.spmm(index, value, m, n, matrix)
 
 

@@ -8,6 +8,7 @@ from typing import Optional, Tuple
 
 import torch
 
+from gno_b200 import autograd as _ag
 from gno_b200 import ops as _ops
 
 
@@ -26,7 +27,9 @@ class SparseTensor:
             sparse_sizes = (m, n)
         self._sizes = (int(sparse_sizes[0]), int(sparse_sizes[1]))
         if row is not None and not is_sorted and row.numel() > 1:
-            index, value = _ops.coalesce(torch.stack([row, col]), value, self._sizes[0], self._sizes[1])
+            # upstream SparseStorage sorts by row*n+col and keeps duplicate entries (a multigraph's
+            # parallel edges count separately in matmul / nnz): sort only, never merge
+            index, value = _ops.sort_coo(torch.stack([row, col]), value, self._sizes[0], self._sizes[1])
             row, col = index[0], index[1]
             rowptr = None
         self._row, self._col, self._value, self._rowptr = row, col, value, rowptr
@@ -120,7 +123,11 @@ def matmul(src: SparseTensor, other: torch.Tensor, reduce: str = "sum") -> torch
     rowptr, col, value = src.csr()
     squeeze = other.dim() == 1
     mat = other.unsqueeze(-1) if squeeze else other
-    if reduce in ("min", "max") and value is not None:
-        raise NotImplementedError("gno_b200 matmul: min/max with edge values is not supported")
-    out = _ops.spmm_csr(rowptr, col, value, mat, "sum" if reduce == "add" else reduce)
+    reduce = "sum" if reduce == "add" else reduce
+    needs_grad = torch.is_grad_enabled() and (mat.requires_grad or (value is not None and value.requires_grad))
+    if needs_grad:  # backward = the transposed aggregation (plan on col, cached like upstream's csr2csc)
+        out = _ag.spmm_csr(rowptr, col, value, mat, reduce)
+        out = out[0] if reduce in ("min", "max") else out
+    else:
+        out = _ops.spmm_csr(rowptr, col, value, mat, reduce)
     return out.squeeze(-1) if squeeze else out

@@ -232,15 +232,18 @@ int gno_gather_rows(const void* x, int64_t x_rows, int64_t row_bytes,
  * row row_off[q] + slot - seg[q].  serve_rows == NULL sends row slot - seg[q]
  * (every peer receives all local rows: an all-gather by peer stores).  Slots are served in rotated order starting
  * at start_slot (pass seg[(rank+1) % n_peers]) so that at any moment the ranks
- * push to different receivers.  Replaces "gather into a send buffer, then
- * all-to-all"; the caller provides the cross-rank barrier (new work, no
- * reference counterpart: the reference is single-GPU).
+ * push to different receivers.  max_blocks > 0 caps the grid: posted peer
+ * stores keep NVLink busy from a few warps per SM, and a small grid leaves the
+ * SM slots to a reduction running beside it on another stream (0 = fill the
+ * chip).  Replaces "gather into a send buffer, then all-to-all"; the caller
+ * provides the cross-rank barrier (new work, no reference counterpart: the
+ * reference is single-GPU).
  */
 int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes,
                   const int64_t* serve_rows, int64_t n_serve, int n_peers,
                   void* const* peer_bufs, const int64_t* seg,
                   const int64_t* row_off, int64_t dst_stride_bytes,
-                  int64_t start_slot, gno_stream_t stream);
+                  int64_t start_slot, int max_blocks, gno_stream_t stream);
 
 /* -------------------------------------------- element-wise index form -- */
 /*
@@ -274,7 +277,9 @@ int gno_scatter_elementwise(const void* src, const int64_t* index, int64_t B,
  * rows of K elements).  Outputs are sized for E entries; *nnz_out (device
  * int64) receives the merged count.  Passing (col,row,n,m) gives
  * torch_sparse.transpose.  flags: bit0 = input known sorted by `row`
- * (sort only the low key bits).
+ * (sort only the low key bits); bit1 = sort only, duplicate (row, col) entries
+ * stay separate (torch_sparse.SparseStorage's construction order: it sorts by
+ * row*n+col and never merges).
  * Reference call site: op_bm_scripts/benchmark_sparse_coalesce.py:35-37;
  * transpose: data/sparse_transpose.csv rows (torch_sparse.transpose).
  */

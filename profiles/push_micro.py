@@ -33,11 +33,12 @@ for order in ("sequential", "random"):
     ptrs = (ctypes.c_void_p * P)(*[int(hdl.buffer_ptrs[q]) for q in range(P)])
     segc = (ctypes.c_int64 * (P + 1))(*seg); off = (ctypes.c_int64 * P)(*([0] * P))
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    def push():
-        check(lib.gno_push_rows(ctypes.c_void_p(x.data_ptr()), F * es, F * es, ctypes.c_void_p(serve.data_ptr()), rows, P,
-                                ptrs, segc, off, F * es, 0, st))
-    t = timed(push)
-    if rank == 0: print("push kernel", order, "GB/s", rows * F * es / t / 1e6, flush=True)
+    for max_blocks in (0, 1184, 592, 296, 148, 74):   # grid cap: how few CTAs still saturate NVLink?
+        def push():
+            check(lib.gno_push_rows(ctypes.c_void_p(x.data_ptr()), F * es, F * es, ctypes.c_void_p(serve.data_ptr()), rows, P,
+                                    ptrs, segc, off, F * es, 0, max_blocks, st))
+        t = timed(push)
+        if rank == 0: print("push kernel", order, "max_blocks", max_blocks, "GB/s", rows * F * es / t / 1e6, flush=True)
     def push_bar():
         hdl.barrier(channel=0); push(); hdl.barrier(channel=1)
     t = timed(push_bar)

@@ -30,7 +30,8 @@ def main():
     ap.add_argument("--workload", default="rmat26")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--row-weight", type=int, default=4)
-    ap.add_argument("--settings", default="push:1;push:2;push:4;push:4:0.1,0.2,0.3,0.4;push:8;needed:4")
+    ap.add_argument("--settings", default="push:1;push:2::source;push:3:0.1,0.9:source;push:4:0.05,0.25,0.7:source",
+                    help="';'-separated exchange:stages[:fracs[:split[:ownership[:push_blocks]]]]")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -72,11 +73,15 @@ def main():
         parts = setting.split(":")
         mode, K = parts[0], int(parts[1])
         fracs = [float(v) for v in parts[2].split(",")] if len(parts) > 2 and parts[2] else None
+        split = parts[3] if len(parts) > 3 and parts[3] else "dest"
+        own = parts[4] if len(parts) > 4 and parts[4] else "cyclic"
+        pblocks = int(parts[5]) if len(parts) > 5 and parts[5] else 296
         gno_b200.clear_caches()
         torch.cuda.empty_cache()
         t0 = time.perf_counter()
         agg = DistAggregator(bounds, src, dst, rank=rank, world=world, cyclic_rows=N, exchange=mode, stages=K,
-                             stage_fracs=fracs, row_weight=args.row_weight)
+                             stage_fracs=fracs, row_weight=args.row_weight, split=split, ownership=own,
+                             push_blocks=pblocks)
         plans = agg.xstage_plans()
         if mode == "push":
             recv = agg._push_buffer(F, dtype, dev)[0][:agg.n_needed]
@@ -86,27 +91,36 @@ def main():
         setup_s = time.perf_counter() - t0
         step_ms = timed(lambda: agg.aggregate(x_local, "sum", x_full=recv if mode == "needed" else None, out=out),
                         args.steps)
+        # timeline of one staged step on every rank (events on both streams, ms from the step start)
+        timeline = None
+        if K > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+            agg.trace = []
+            agg.aggregate(x_local, "sum", x_full=recv if mode == "needed" else None, out=out)
+            torch.cuda.synchronize()
+            t0e = agg.trace[0][1]
+            timeline = {lab: round(t0e.elapsed_time(e), 3) for lab, e in agg.trace[1:]}
+            agg.trace = None
+            if rank != 0:
+                print(json.dumps({"rank": rank, "timeline_ms": timeline}), flush=True)
         xonly = timed((lambda: agg.exchange_push(x_local)) if mode == "push" else
                       (lambda: agg.exchange_needed(x_local, recv)), args.steps)
 
-        def reduce_only():
-            for p, g_, _, r0, r1 in plans:
-                if r1 > r0:
-                    gno_b200.segment_reduce(p, recv, "sum", gidx=g_, out=out[r0:r1])
-        ronly = timed(reduce_only, args.steps)
+        ronly = timed(lambda: agg.reduce_stages(recv, "sum", out), args.steps)
         info = torch.tensor([agg.n_needed, agg.n_needed - agg.recv_splits[rank], src.numel()], device=dev,
                             dtype=torch.float64)
         mx = info.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(json.dumps({"workload": args.workload, "n_gpus": world, "exchange": mode, "stages": K,
-                              "stage_fracs": fracs, "step_ms": round(step_ms, 3),
+            print(json.dumps({"workload": args.workload, "n_gpus": world, "exchange": mode, "stages": K, "split": split, "ownership": own, "push_blocks": pblocks,
+                              "stage_fracs": fracs, "stage_edges_rank0": [p.E for p, *_ in plans], "step_ms": round(step_ms, 3),
                               "exchange_only_ms": round(xonly, 3), "reduce_only_ms": round(ronly, 3),
                               "edges_per_s": E / (step_ms * 1e-3),
                               "recv_rows_max": int(mx[0]), "remote_rows_max": int(mx[1]),
                               "remote_GB_max": round(float(mx[1]) * F * 2 / 1e9, 3), "edges_max": int(mx[2]),
                               "stage_recv_rows_rank0": [agg.stage_row0[s + 1] - agg.stage_row0[s] for s in range(K)],
-                              "setup_s": round(setup_s, 1)}), flush=True)
+                              "setup_s": round(setup_s, 1), "timeline_ms_rank0": timeline}), flush=True)
         del agg, plans, recv
     dist.destroy_process_group()
 

@@ -99,6 +99,40 @@ def _worker(rank, world, port, N, E, F, ret):
             dist.all_gather(allr, mine)
             for q in range(world):
                 ok &= [allr[q][s][rank].item() for s in range(3)] == [aggs.put_off[s][q] for s in range(3)]
+        # source split: stage 0 = own rows, then remote rows by decreasing reference count; a stage
+        # reduces the edges whose source lies in its group, accumulating over all rows
+        for K, fr in ((2, None), (4, [0.1, 0.3, 0.6])):
+            aggs = DistAggregator(bounds, s_r, d_r, exchange="needed", cyclic_rows=N, stages=K, stage_fracs=fr,
+                                  split="source")
+            recv = aggs.exchange_needed(x[rank::world].contiguous(), gather_rows=lambda t, r: t.index_select(0, r))
+            ok &= recv.size(0) == torch.unique(s_r).numel()
+            ok &= aggs.recv_cnt[0][1 - rank] == 0 and aggs.serve_cnt[0][1 - rank] == 0   # stage 0 stays on this rank
+            ok &= all(aggs.recv_cnt[s][rank] == 0 for s in range(1, K))                   # remote stages hold no own row
+            got = torch.zeros(hi - lo, F)
+            refs_prev = None
+            for s in range(K):
+                m = aggs.stage_of_edge == s
+                if m.any():
+                    ok &= int(aggs.src_needed[m].min()) >= aggs.stage_row0[s]
+                    ok &= int(aggs.src_needed[m].max()) < aggs.stage_row0[s + 1]
+                    got += oracle.gather_scatter(recv, aggs.src_needed[m], d_r[m], hi - lo, "sum")[0]
+                    if s >= 1:  # groups are ordered by decreasing reference count
+                        refs = torch.bincount(aggs.src_needed[m] - aggs.stage_row0[s])
+                        refs = refs[refs > 0]
+                        if refs_prev is not None and refs.numel():
+                            ok &= int(refs.max()) <= refs_prev
+                        if refs.numel():
+                            refs_prev = int(refs.min())
+            ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
+        # xorfold ownership (balanced on ids with skewed bits): pad the feature rows to an even count
+        from gno_b200.dist import xorfold_global_ids
+        xp = torch.cat([x, torch.zeros(N % 2, F)])
+        aggx = DistAggregator(bounds, s_r, d_r, exchange="needed", cyclic_rows=xp.size(0), ownership="xorfold",
+                              stages=3, stage_fracs=[0.5, 0.5], split="source")
+        mine = xorfold_global_ids(rank, world, xp.size(0) // world)
+        recv = aggx.exchange_needed(xp[mine].contiguous(), gather_rows=lambda t, r: t.index_select(0, r))
+        got, _ = oracle.gather_scatter(recv, aggx.src_needed, d_r, hi - lo, "sum")
+        ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
         ret[rank] = (bool(ok), int(d_r.numel()))
     finally:
         dist.destroy_process_group()
@@ -124,3 +158,25 @@ def test_edge_balanced_ranges():
     assert sum(per) == 300 and max(per) <= 200
     assert edge_balanced_ranges(torch.zeros(0, dtype=torch.int64), 4).tolist() == [0, 0, 0, 0, 0]
     assert edge_balanced_ranges(torch.tensor([5]), 2).tolist()[-1] == 1
+
+
+def test_xorfold_ownership_is_a_balanced_bijection():
+    from gno_b200.dist import xorfold_global_ids, xorfold_owner
+    for world in (1, 2, 4, 8):
+        n = 1 << 10
+        ids = torch.arange(n)
+        owner, local = xorfold_owner(ids, world)
+        assert int(owner.min()) >= 0 and int(owner.max()) < world
+        assert torch.bincount(owner, minlength=world).tolist() == [n // world] * world
+        assert torch.unique(owner * (n // world) + local).numel() == n          # (owner, local) is a bijection
+        for q in range(world):
+            g = xorfold_global_ids(q, world, n // world)
+            o2, l2 = xorfold_owner(g, world)
+            assert bool((o2 == q).all()) and torch.equal(l2, torch.arange(n // world))
+    # ids whose bits are 1 with probability 0.24 (R-MAT): cyclic ownership is skewed, xorfold is not
+    g = torch.Generator().manual_seed(0)
+    bits = (torch.rand(200_000, 20, generator=g) < 0.24).long()
+    ids = (bits << torch.arange(20)).sum(1)
+    cyc = torch.bincount(ids % 2, minlength=2).double() / ids.numel()
+    xf = torch.bincount(xorfold_owner(ids, 2)[0], minlength=2).double() / ids.numel()
+    assert cyc.max() > 0.7 and xf.max() < 0.52

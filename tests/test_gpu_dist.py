@@ -87,6 +87,24 @@ def _worker(rank, world, port, ret):
                 ok &= torch.equal(mapped, warg[lo:hi])
                 got = aggs.aggregate(xl, "sum")
                 ok &= torch.allclose(got.cpu(), wsum[lo:hi], rtol=1e-5, atol=1e-3)
+        # source split (own rows first, then remote rows by decreasing reference count; stages accumulate)
+        wmean, _ = oracle.gather_scatter(x, src, dst, N, "mean")
+        for mode, K, fr in (("push", 2, None), ("push", 4, [0.1, 0.3, 0.6]), ("needed", 3, [0.2, 0.8])):
+            aggs = DistAggregator(bounds, shards[rank][0].to(dev), shards[rank][1].to(dev), exchange=mode,
+                                  cyclic_rows=N, stages=K, stage_fracs=fr, split="source")
+            xl = x[rank::world].contiguous().to(dev)
+            for _ in range(3):
+                ok &= torch.allclose(aggs.aggregate(xl, "sum").cpu(), wsum[lo:hi], rtol=1e-5, atol=1e-3)
+                ok &= torch.allclose(aggs.aggregate(xl, "mean").cpu(), wmean[lo:hi], rtol=1e-5, atol=1e-3)
+        # xorfold ownership + a capped push grid (the exchange shares the SMs with the reduction)
+        from gno_b200.dist import xorfold_global_ids
+        xp = torch.cat([x, torch.zeros(N % 2, F)])
+        aggx = DistAggregator(bounds, shards[rank][0].to(dev), shards[rank][1].to(dev), exchange="push",
+                              cyclic_rows=xp.size(0), ownership="xorfold", stages=3, stage_fracs=[0.3, 0.7],
+                              split="source", push_blocks=8)
+        xl = xp[xorfold_global_ids(rank, world, xp.size(0) // world)].contiguous().to(dev)
+        for _ in range(3):
+            ok &= torch.allclose(aggx.aggregate(xl, "sum").cpu(), wsum[lo:hi], rtol=1e-5, atol=1e-3)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
@@ -131,6 +149,11 @@ def _worker_world1(rank, world, port, ret):
                 gm, ga = agg.aggregate(x.to(dev), "max", return_arg=True)
                 ok &= torch.equal(gm.float().cpu(), wmax)
                 ok &= torch.equal(ga.cpu(), warg)
+        # source split on one rank: every row is this rank's own, the remote stages are empty
+        agg = DistAggregator(bounds, src.to(dev), dst.to(dev), rank=0, world=1, exchange="push", cyclic_rows=N,
+                             stages=3, stage_fracs=[0.1, 0.9], split="source")
+        for _ in range(2):
+            ok &= torch.allclose(agg.aggregate(x.to(dev), "sum").float().cpu(), wsum, rtol=1e-2, atol=1e-2)
         ret[0] = bool(ok)
     finally:
         dist.destroy_process_group()

@@ -690,3 +690,101 @@ def test_scatter_out_forms(cuda, full_shape):
         else:
             assert got.data_ptr() == o.data_ptr()
             assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-5), red
+
+
+# ---- segment_csr / gather_csr with N-D and sub-range indptr --------------------------------------
+def _segment_ref(src, ptr, dim, reduce):
+    """Python restatement of torch_scatter.segment_csr for one pointer row per leading index:
+    out[..., m, :] reduces src[..., ptr[..., m]:ptr[..., m+1], :]; empty segments give 0 / arg = E."""
+    lead = list(src.shape[:dim])
+    E, M = src.size(dim), ptr.size(-1) - 1
+    s3 = src.reshape(-1, E, int(torch.tensor(src.shape[dim + 1:]).prod()) if src.dim() > dim + 1 else 1)
+    p2 = ptr.expand(lead + [M + 1]).reshape(-1, M + 1)
+    out = torch.zeros(s3.size(0), M, s3.size(2))
+    arg = torch.full((s3.size(0), M, s3.size(2)), E, dtype=torch.int64)
+    for b in range(s3.size(0)):
+        for m in range(M):
+            a, z = int(p2[b, m]), int(p2[b, m + 1])
+            if z <= a:
+                continue
+            seg = s3[b, a:z]
+            if reduce == "sum":
+                out[b, m] = seg.sum(0)
+            elif reduce == "mean":
+                out[b, m] = seg.mean(0)
+            else:
+                v, i = (seg.max(0) if reduce == "max" else seg.min(0))
+                out[b, m] = v
+                # lowest position among ties, like the sequential upstream loop
+                hit = seg == v.unsqueeze(0)
+                arg[b, m] = hit.float().argmax(0) + a
+    shape = lead + [M] + list(src.shape[dim + 1:])
+    return out.view(shape), arg.view(shape)
+
+
+def test_segment_csr_upstream_docstring_example(cuda):
+    """torch_scatter's own docstring: src [10, 6, 64], indptr [1, 4] broadcast over dim 0."""
+    import torch_scatter
+    g = torch.Generator().manual_seed(1)
+    src = torch.randn(10, 6, 64, generator=g)
+    indptr = torch.tensor([0, 2, 5, 6]).view(1, -1)
+    out = torch_scatter.segment_csr(src.to(cuda), indptr.to(cuda), reduce="sum")
+    assert list(out.shape) == [10, 3, 64]
+    want = torch.stack([src[:, 0:2].sum(1), src[:, 2:5].sum(1), src[:, 5:6].sum(1)], 1)
+    assert torch.allclose(out.cpu(), want, rtol=1e-5, atol=1e-5)
+    back = torch_scatter.gather_csr(out, indptr.to(cuda))
+    assert list(back.shape) == [10, 6, 64]
+    assert torch.equal(back[:, 3].cpu(), out[:, 1].cpu()) and torch.equal(back[:, 5].cpu(), out[:, 2].cpu())
+
+
+@pytest.mark.parametrize("reduce", ["sum", "mean", "min", "max"])
+def test_segment_csr_nd_and_subrange_indptr(cuda, reduce):
+    import gno_b200
+    g = torch.Generator().manual_seed(12)
+    src = (torch.randn(4, 3, 50, 7, generator=g) * 4).round() / 4
+    cases = {
+        # shared pointers with empty segments, covering only [5, 40) of the dim
+        "shared_subrange": torch.tensor([5, 5, 9, 20, 20, 40]).view(1, 1, -1),
+        # one pointer row per batch, every batch covers its whole dim (flat-rowptr path)
+        "per_batch_full": torch.stack([torch.cat([torch.zeros(1, dtype=torch.long),
+                                                  torch.sort(torch.randint(0, 51, (5,), generator=g)).values,
+                                                  torch.full((1,), 50)]) for _ in range(12)]).view(4, 3, 7),
+        # one pointer row per batch with gaps before the first / after the last pointer
+        "per_batch_gaps": torch.stack([torch.sort(torch.randint(0, 51, (6,), generator=g)).values
+                                       for _ in range(12)]).view(4, 3, 6),
+    }
+    for name, ptr in cases.items():
+        want, warg = _segment_ref(src, ptr, 2, reduce)
+        got = gno_b200.segment_csr(src.to(cuda), ptr.to(cuda), None, reduce, return_arg=True)
+        if reduce in ("min", "max"):
+            assert torch.equal(got[0].cpu(), want), name
+            assert torch.equal(got[1].cpu(), warg), name
+        else:
+            assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-5), name
+    # 1-D indptr over a sub-range of dim 0 (elements outside it are ignored)
+    s2 = (torch.randn(60, 5, generator=g) * 4).round() / 4
+    p1 = torch.tensor([7, 7, 20, 33, 33, 51])
+    want, warg = _segment_ref(s2, p1, 0, reduce)
+    got = gno_b200.segment_csr(s2.to(cuda), p1.to(cuda), None, reduce, return_arg=True)
+    if reduce in ("min", "max"):
+        assert torch.equal(got[0].cpu(), want) and torch.equal(got[1].cpu(), warg)
+    else:
+        assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-5)
+
+
+def test_gather_csr_nd(cuda):
+    import gno_b200
+    g = torch.Generator().manual_seed(13)
+    src = torch.randn(3, 4, 6, generator=g)
+    shared = torch.tensor([0, 2, 2, 5, 9]).view(1, -1)
+    got = gno_b200.gather_csr(src.to(cuda), shared.to(cuda)).cpu()
+    rows = torch.repeat_interleave(torch.arange(4), shared[0, 1:] - shared[0, :-1])
+    assert torch.equal(got, src[:, rows])
+    per = torch.tensor([[0, 1, 4, 4, 6], [0, 0, 3, 5, 6], [0, 2, 2, 2, 6]])
+    got = gno_b200.gather_csr(src.to(cuda), per.to(cuda)).cpu()
+    for b in range(3):
+        rows = torch.repeat_interleave(torch.arange(4), per[b, 1:] - per[b, :-1])
+        assert torch.equal(got[b], src[b, rows])
+    with pytest.raises(ValueError):
+        gno_b200.spmm_csr(torch.tensor([0, 2, 3]).to(cuda), torch.zeros(5, dtype=torch.long).to(cuda), None,
+                          torch.ones(4, 2).to(cuda))
