@@ -524,7 +524,7 @@ def run_rmat(args):
     ka.record()
     for _ in range(args.steps):
         if world > 1:
-            agg.reduce_stages(x_gather, "sum", out)
+            agg.reduce_stages(x_gather, "sum", out, x_local=x_local)
         else:
             gno_b200.segment_reduce(plan, x_gather, "sum", gidx=gidx, out=out)
     kb.record()
@@ -988,7 +988,7 @@ def main():
                     help="rmat workloads at N>1: feature row i lives on rank i %% N (cyclic) or on the XOR of "
                          "the log2(N)-bit groups of i (xorfold: balanced on R-MAT ids, whose bits are skewed); "
                          "auto = xorfold for power-of-two N")
-    ap.add_argument("--push-blocks", type=int, default=296,
+    ap.add_argument("--push-blocks", type=int, default=148,
                     help="grid cap of the push kernel when it runs beside the reduction (0 = fill the chip)")
     ap.add_argument("--per-config", type=int, default=1,
                     help="N=1: also time the other BASELINE.json configs' kernels (per_config object)")

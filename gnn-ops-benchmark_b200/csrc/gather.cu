@@ -135,6 +135,86 @@ __global__ void __launch_bounds__(256) push_rows_kernel(const PushParams p) {
 }
 
 
+// ---- TMA-staged push ---------------------------------------------------------------------------
+// The same exchange driven by the TMA engine instead of by warps of loads and stores.  One warp
+// per CTA: its lanes issue one 1-D bulk copy per requested row (global -> shared, completion on
+// an mbarrier), and as soon as a chunk of rows has landed ONE bulk copy stores the whole chunk —
+// the rows are consecutive in the requester's buffer — from shared memory into the peer's HBM
+// over NVLink (cp.async.bulk.global.shared::cta).  A 4-stage ring keeps two chunks of gathers and
+// two chunk stores in flight per CTA.  What matters is what the kernel does NOT hold: 32 threads
+// and a few registers per SM.  The LDG/STG form needs 300-600 CTAs of 256 threads to saturate
+// NVLink (profiles/scaling/r2e_push_micro_grid_cap.txt) and, resident beside the reduction, took
+// half of its warp slots and registers: the reduction of the overlapped stage ran 13.7 ms instead
+// of 10.3 (profiles/scaling/r2g_*).
+constexpr int kTmaStages = 4;
+constexpr int kTmaAhead = 2;            // chunks of gathers in flight ahead of the chunk being stored
+constexpr int kTmaChunkBytes = 16384;
+
+struct PushTmaParams {
+  PushParams b;
+  int64_t chunk0[kMaxPeers + 1];  // chunk0[q] = first chunk of requester q (chunks never straddle requesters)
+  int64_t start_chunk;            // rotation, so the ranks store to different receivers at any moment
+  int rows_per_chunk;
+};
+
+__global__ void __launch_bounds__(32) push_rows_tma_kernel(const PushTmaParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);            // kTmaStages barriers
+  unsigned char* buf = smem_raw + 128;                                // kTmaStages chunk buffers
+  const int lane = threadIdx.x;
+  const int R = p.rows_per_chunk;
+  const uint32_t rb = (uint32_t)p.b.row_bytes;
+  const int64_t n_chunks = p.chunk0[p.b.P];
+  if (lane == 0) {
+    for (int i = 0; i < kTmaStages; ++i) mbar_init(bar + i, 1);
+  }
+  __syncwarp();
+  const int64_t first = blockIdx.x, step = gridDim.x;
+  const int64_t n_my = first < n_chunks ? (n_chunks - first + step - 1) / step : 0;
+
+  auto locate = [&](int64_t it, int& q, int64_t& slot0, int& rows) {
+    int64_t c = first + it * step + p.start_chunk;
+    if (c >= n_chunks) c -= n_chunks;
+    q = 0;
+    while (q + 1 < p.b.P && c >= p.chunk0[q + 1]) ++q;
+    slot0 = p.b.seg[q] + (c - p.chunk0[q]) * R;
+    rows = (int)imin64(R, p.b.seg[q + 1] - slot0);
+  };
+
+  for (int64_t it = 0; it < n_my + kTmaAhead; ++it) {
+    if (it < n_my) {  // gather chunk `it` into its ring slot
+      const int st = (int)(it % kTmaStages);
+      // the slot was last read by the store of chunk it - kTmaStages, committed two iterations ago
+      if (lane == 0) bulk_wait_read<kTmaStages - kTmaAhead - 1>();
+      __syncwarp();
+      int q, rows;
+      int64_t slot0;
+      locate(it, q, slot0, rows);
+      if (lane == 0) mbar_expect_tx(bar + st, (uint32_t)rows * rb);
+      __syncwarp();
+      unsigned char* dst = buf + (size_t)st * kTmaChunkBytes;
+      for (int r = lane; r < rows; r += 32) {
+        const int64_t row = p.b.serve_rows[slot0 + r];
+        bulk_g2s(dst + (size_t)r * rb, p.b.x + row * p.b.src_stride, rb, bar + st);
+      }
+    }
+    const int64_t j = it - kTmaAhead;  // chunk whose rows have had two iterations to arrive
+    if (j >= 0) {
+      const int st = (int)(j % kTmaStages);
+      mbar_wait(bar + st, (uint32_t)((j / kTmaStages) & 1));
+      if (lane == 0) {
+        int q, rows;
+        int64_t slot0;
+        locate(j, q, slot0, rows);
+        char* out = p.b.peer_buf[q] + (p.b.row_off[q] + (slot0 - p.b.seg[q])) * p.b.dst_stride;
+        bulk_s2g(out, buf + (size_t)st * kTmaChunkBytes, (uint32_t)rows * rb);
+        bulk_commit();
+      }
+    }
+  }
+  if (lane == 0) bulk_wait_all();  // every store has been performed before the kernel ends
+}
+
 // Batched 2-D transpose out[o, c, r] = in[o, r, c] through a padded 32x32 shared-memory tile
 // (coalesced on both sides).  Moves the sorted dim of an inner-dim torch.sort last and back.
 template <typename V>
@@ -278,6 +358,41 @@ int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes, co
   p.seg[n_peers] = seg[n_peers];
   GNO_CHECK_ARG(seg[0] == 0 && seg[n_peers] == n_serve, "gno_push_rows: seg must cover [0, n_serve)");
   cudaStream_t s = (cudaStream_t)stream;
+  // TMA-staged form: rows gathered by index, 16-byte aligned, destination rows contiguous
+  static const int tma_env = getenv("GNO_PUSH_TMA") ? atoi(getenv("GNO_PUSH_TMA")) : 1;
+  // (chosen when the caller caps the grid, i.e. the exchange runs beside the reduction; alone on
+  // the chip the LDG/STG form is faster: 4.4 vs 6.2 ms for RMAT-26's exchange at P=2, where half of
+  // the rows are local copies that move at HBM speed)
+  if (tma_env && max_blocks > 0 && serve_rows != nullptr && a % 16 == 0 && dst_stride_bytes == row_bytes &&
+      row_bytes <= kTmaChunkBytes / 4) {
+    PushTmaParams t;
+    t.b = p;
+    t.rows_per_chunk = (int)(kTmaChunkBytes / row_bytes);
+    t.chunk0[0] = 0;
+    for (int q = 0; q < n_peers; ++q)
+      t.chunk0[q + 1] = t.chunk0[q] + ceil_div(seg[q + 1] - seg[q], (int64_t)t.rows_per_chunk);
+    const int64_t n_chunks = t.chunk0[n_peers];
+    // start at the requester the LDG/STG form starts at: the first chunk of the segment holding start_slot
+    int q0 = 0;
+    while (q0 + 1 < n_peers && p.start >= seg[q0 + 1]) ++q0;
+    t.start_chunk = n_chunks > 0 ? t.chunk0[q0] % n_chunks : 0;
+    const size_t smem = 128 + (size_t)kTmaStages * kTmaChunkBytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+      GNO_CUDA(cudaFuncSetAttribute(push_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    // one warp per SM drives 617 GB/s, two 677 GB/s (profiles/scaling/r2h_push_micro_tma.txt);
+    // each CTA holds 64 KB of shared memory, so the second one costs the reduction occupancy
+    int64_t blocks = (int64_t)kNumSMs * 2;
+    if (max_blocks < blocks) blocks = max_blocks;
+    if (blocks > n_chunks) blocks = n_chunks;
+    if (blocks > 0) {
+      push_rows_tma_kernel<<<(unsigned)blocks, 32, smem, s>>>(t);
+      GNO_LAUNCHED("push_rows_tma_kernel");
+    }
+    return GNO_OK;
+  }
   const int64_t cap = max_blocks > 0 ? (int64_t)max_blocks : (int64_t)kNumSMs * 32;
   auto grid = [cap](int64_t n) {
     int64_t b = ceil_div(n, 256);

@@ -363,6 +363,9 @@ __device__ __forceinline__ void flush_acc(const SegParams& p, int row, int chunk
 template <typename T, int VB, int RED, bool ARG, bool HAS_W, int U>
 __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMinBlocks - 1 : kSegMinBlocks)
     segreduce_kernel(const SegParams p) {
+  // programmatic dependent launch: the finish kernel may become resident while the last wave runs
+  // (it fills the empty rows, then waits for this grid before touching the chunk partials)
+  asm volatile("griddepcontrol.launch_dependents;");
   constexpr int EPV = VB / (int)sizeof(T);
   const int lane = threadIdx.x & 31;
   const int G = p.G;
@@ -526,38 +529,10 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
 // memory; the warps then read records with broadcast LDS instead of per-tile global loads and
 // shuffles.  No warp-synchronous operation is left in the loop, so every worker follows its own
 // row boundaries without dragging the other workers of its warp through the slow path.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-
 template <typename T, int VB, int RED, bool ARG, bool HAS_W, int U>
 __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMinBlocks - 1 : kSegMinBlocks)
     segreduce_staged_kernel(const SegParams p) {
+  asm volatile("griddepcontrol.launch_dependents;");  // see segreduce_kernel
   constexpr int EPV = VB / (int)sizeof(T);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -712,8 +687,17 @@ __global__ void __launch_bounds__(256) segfinish_kernel(const SegParams p) {
   const int64_t total = n_a + (p.accumulate ? 0 : p.n_empty * per_empty);
   const bool vec_val = ((uintptr_t)p.out % (4 * sizeof(T)) == 0) && (p.ldo_bytes % (4 * sizeof(T)) == 0);
   const bool vec_arg = ARG && p.arg && ((uintptr_t)p.arg % 16 == 0) && (p.F % 2 == 0);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  // Phase 1 (items >= n_a): empty rows, which no chunk of the main kernel writes.  Phase 2 (items
+  // < n_a): rows cut by a chunk boundary, after griddepcontrol.wait — the main grid has completed
+  // and its partials are visible.  Launched with programmatic stream serialization, phase 1 and
+  // this kernel's launch latency overlap the tail of the main kernel.
+  const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tstride = (int64_t)gridDim.x * blockDim.x;
+  for (int phase = 0; phase < 2; ++phase) {
+  if (phase == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int64_t i_begin = phase == 0 ? n_a + tid0 : tid0;
+  const int64_t i_end = phase == 0 ? total : n_a;
+  for (int64_t i = i_begin; i < i_end; i += tstride) {
     if (i >= n_a && fill16) {
       const int64_t j = i - n_a;
       int64_t z, c;
@@ -843,6 +827,7 @@ __global__ void __launch_bounds__(256) segfinish_kernel(const SegParams p) {
       }
     }
   }
+  }  // phase
 }
 
 // ------------------------------------------------------------- dispatch --
@@ -877,7 +862,22 @@ static int launch_seg(const SegParams& p, cudaStream_t s) {
   const int64_t total = p.n_span * quads + (p.accumulate ? 0 : p.n_empty * per_empty);
   if (total > 0) {
     const int grid = (int)imin64(ceil_div(total, 256), (int64_t)kNumSMs * 16);
-    segfinish_kernel<T, RED, ARG><<<grid, 256, 0, s>>>(p);
+    static const int pdl_env = getenv("GNO_SEG_PDL") ? atoi(getenv("GNO_SEG_PDL")) : 1;
+    if (blocks > 0 && pdl_env) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)grid);
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      GNO_CUDA(cudaLaunchKernelEx(&cfg, segfinish_kernel<T, RED, ARG>, p));
+    } else {
+      segfinish_kernel<T, RED, ARG><<<grid, 256, 0, s>>>(p);
+    }
     GNO_LAUNCHED("segfinish_kernel");
   }
   return GNO_OK;

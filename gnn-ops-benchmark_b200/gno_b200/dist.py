@@ -107,7 +107,7 @@ class DistAggregator:
 
     def __init__(self, bounds, src_global, dst_local, rank=None, world=None, group=None, stages=1,
                  feature_bounds=None, exchange="allgather", cyclic_rows=None, stage_fracs=None,
-                 row_weight=0, split="dest", ownership="cyclic", push_blocks=296):
+                 row_weight=0, split="dest", ownership="cyclic", push_blocks=148):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -226,6 +226,7 @@ class DistAggregator:
                 first[by_refs[cuts[s_ - 1]:cuts[s_]]] = s_
             self.sub_bounds = None
             self.stage_of_edge = first[inv]
+            self.src_local = local       # stage 0 gathers this rank's own rows straight from x_local
         elif K > 1:
             counts = torch.bincount(self.dst_local, minlength=self.n_out) + self.row_weight
             self.sub_bounds = stage_ranges(counts, K, self.stage_fracs).cpu()
@@ -477,23 +478,29 @@ class DistAggregator:
                 else:
                     lo, hi, acc = int(self.sub_bounds[s]), int(self.sub_bounds[s + 1]), False
                 p = planmod.build_plan(self.dst_local[where] - lo, hi - lo)
-                gidx = p.sorted_ids(self.src_needed[where])
+                own = self.split == "source" and s == 0   # rows of x_local, not of the receive buffer
+                gidx = p.sorted_ids((self.src_local if own else self.src_needed)[where])
                 eid = p.sorted_ids(where)
                 self._stage_plans.append((p, gidx, eid, lo, hi, acc))
         return self._stage_plans
 
-    def reduce_stages(self, recv, reduce, out, want_arg=False, arg=None, events=None):
+    def reduce_stages(self, recv, reduce, out, want_arg=False, arg=None, events=None, x_local=None):
         """The local half of a staged step: every stage plan over the receive buffer (waiting for
-        events[s] first when given).  Also what bench.py times as the kernel-only loop."""
+        events[s] first when given; split="source" reads stage 0 from x_local and waits for
+        nothing).  Also what bench.py times as the kernel-only loop."""
         from . import ops
         cur = torch.cuda.current_stream(recv.device)
+        own0 = self.split == "source" and self.xstages > 1
+        if own0 and x_local is None:
+            raise ValueError("split='source' reduces stage 0 from x_local")
         for s, (p, gidx, eid, lo, hi, acc) in enumerate(self.xstage_plans()):
-            if events is not None:
+            if events is not None and not (own0 and s == 0):
                 cur.wait_event(events[s])
             self._mark(f"reduce{s} start", cur)
             if hi == lo or (acc and p.E_valid == 0):
                 continue
-            r = ops.segment_reduce(p, recv, reduce, gidx=gidx, eid=eid, want_arg=want_arg,
+            r = ops.segment_reduce(p, x_local if (own0 and s == 0) else recv, reduce, gidx=gidx, eid=eid,
+                                   want_arg=want_arg,
                                    arg_fill=self.dst_local.numel(), out=out[lo:hi], accumulate=acc)
             if want_arg:
                 arg[lo:hi].copy_(r[1])
@@ -527,7 +534,8 @@ class DistAggregator:
         arg = torch.empty((self.n_out, F), dtype=torch.int64, device=dev) if want_arg else None
         cur = torch.cuda.current_stream(dev)
         if self._push_stream is None:
-            self._push_stream = torch.cuda.Stream(dev, priority=-1)
+            import os
+            self._push_stream = torch.cuda.Stream(dev, priority=int(os.environ.get("GNO_PUSH_PRIORITY", "-1")))
             self._push_events = [torch.cuda.Event() for _ in range(self.xstages + 1)]
         ps, ev = self._push_stream, self._push_events
         ev[-1].record(cur)        # x_local is ready and the previous call's reduction has been issued
@@ -538,8 +546,8 @@ class DistAggregator:
             recv, hdl = st[0][:self.n_needed], st[1]
         else:
             recv = x_full if x_full is not None else torch.empty((self.n_needed, F), dtype=x_local.dtype, device=dev)
-        # split="source": stage 0 holds only rows this rank owns (a local copy into its own
-        # buffer): nothing crosses NVLink, so no cross-rank barrier has to follow it
+        # split="source": stage 0 holds only rows this rank owns; the reduction gathers them straight
+        # from x_local, so stage 0 has no exchange at all (and nothing to wait for)
         local0 = self.split == "source"
         self._mark("step start", cur)
         with torch.cuda.stream(ps):
@@ -547,16 +555,17 @@ class DistAggregator:
                 hdl.barrier(channel=0)      # every peer is done reading its buffer from the previous call
                 self._mark("barrier0 done", ps)
             for s in range(self.xstages):
+                if local0 and s == 0:
+                    continue
                 if push:
                     self._push_stage(x_local, st, s, self.push_blocks)
                     self._mark(f"push{s} done", ps)
-                    if not (local0 and s == 0):
-                        hdl.barrier(channel=1)  # stage s has landed everywhere
-                        self._mark(f"barrier after push{s} done", ps)
+                    hdl.barrier(channel=1)  # stage s has landed everywhere
+                    self._mark(f"barrier after push{s} done", ps)
                 else:
                     self.exchange_needed(x_local, recv, stage=s)
                 ev[s].record(ps)
-        self.reduce_stages(recv, kred, out, want_arg, arg, events=ev)
+        self.reduce_stages(recv, kred, out, want_arg, arg, events=ev, x_local=x_local)
         if reduce == "mean" and self.split == "source":
             if self._row_counts is None:
                 self._row_counts = torch.bincount(self.dst_local, minlength=self.n_out).clamp_(min=1)

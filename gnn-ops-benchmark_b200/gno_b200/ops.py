@@ -204,6 +204,8 @@ def scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum", return_ar
         out = torch.empty(out_shape, dtype=src.dtype, device=src.device)
     arg = None
 
+    if not src.is_floating_point():
+        return _scatter_int(src, idx1d, dim, out, accumulate, N, B, E, K, out_shape, reduce, red, want_arg)
     if idx1d is not None:
         plan = plan_cache.get(idx1d.contiguous() if not idx1d.is_contiguous() else idx1d, N)
         # torch_scatter's out= forms: sum/mul accumulate in the kernel; mean = (out + sum) / count;
@@ -249,6 +251,38 @@ def scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum", return_ar
             check(lib.gno_scatter_elementwise(_ptr(src), _ptr(index), B, E, K, _ptr(out), _ptr(arg),
                                               N, dt, red, 1 if accumulate else 0, _ptr(ws), nbytes.value,
                                               _stream(src.device)))
+    return (out, arg) if want_arg else out
+
+
+def _scatter_int(src, idx1d, dim, out, accumulate, N, B, E, K, out_shape, reduce, red, want_arg):
+    """Integer values (PyG's bookkeeping: scatter_add of ones over the batch vector): exact int64
+    accumulation on the cached plan.  1-D / broadcast index only."""
+    if idx1d is None:
+        raise NotImplementedError("gno_b200: integer scatter covers a 1-D (or broadcast) index")
+    if accumulate and red in (GNO_MIN, GNO_MAX):
+        raise NotImplementedError("gno_b200: integer scatter_min/max with out= is not supported")
+    kind = src.dtype
+    if kind not in (torch.int32, torch.int64):
+        if kind in (torch.int8, torch.int16, torch.uint8, torch.bool):
+            src = src.to(torch.int64)
+            if accumulate:
+                raise NotImplementedError("gno_b200: out= needs int32 / int64 values")
+            out = torch.empty(out_shape, dtype=torch.int64, device=src.device)
+        else:
+            raise GnoError(f"gno_b200: unsupported dtype {kind}")
+    plan = plan_cache.get(idx1d.contiguous(), N)
+    arg = torch.empty(out_shape, dtype=torch.int64, device=src.device) if want_arg else None
+    csr = plan.csr(plan.perm, plan.perm)
+    es = src.element_size()
+    s3, o3 = src.view(B, E, K), out.view(B, N, K)
+    a3 = arg.view(B, N, K) if want_arg else None
+    with torch.cuda.device(src.device):
+        for b in range(B):
+            check(lib.gno_segment_reduce_int(ctypes.byref(csr), _ptr(s3[b]), K, _ptr(o3[b]), K,
+                                             _ptr(a3[b]) if want_arg else None, E, K, es, red,
+                                             1 if accumulate else 0, _stream(src.device)))
+    if kind not in (torch.int32, torch.int64) and kind != torch.bool:
+        out = out.to(kind)
     return (out, arg) if want_arg else out
 
 

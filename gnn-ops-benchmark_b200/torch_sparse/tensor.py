@@ -29,8 +29,18 @@ class SparseTensor:
         if row is not None and not is_sorted and row.numel() > 1:
             # upstream SparseStorage sorts by row*n+col and keeps duplicate entries (a multigraph's
             # parallel edges count separately in matmul / nnz): sort only, never merge
-            index, value = _ops.sort_coo(torch.stack([row, col]), value, self._sizes[0], self._sizes[1])
-            row, col = index[0], index[1]
+            if value is not None and value.requires_grad and torch.is_grad_enabled():
+                # keep the autograd graph: sort the keys with an explicit permutation and reorder the
+                # values by (differentiable) indexing
+                m_, n_ = self._sizes
+                key = row * n_ + col
+                iota = torch.arange(key.numel(), dtype=torch.int32, device=key.device)
+                skey, perm = _ops.sort_pairs(key, iota, 0, max(1, (max(m_ * n_, 1) - 1).bit_length()))
+                row, col = torch.div(skey, n_, rounding_mode="floor"), skey % n_
+                value = value[perm.to(torch.int64)]
+            else:
+                index, value = _ops.sort_coo(torch.stack([row, col]), value, self._sizes[0], self._sizes[1])
+                row, col = index[0], index[1]
             rowptr = None
         self._row, self._col, self._value, self._rowptr = row, col, value, rowptr
         self._t = None

@@ -190,6 +190,18 @@ int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows,
                        gno_stream_t stream);
 
 /*
+ * Integer form (int32 / int64 values, exact int64 accumulation): torch_scatter.scatter on
+ * integer tensors — PyG's TopKPooling / to_dense_batch count nodes per graph with
+ * scatter_add(batch.new_ones(n), batch, dim=0) (graph_benchmark/models/ptg_models.py:165-172).
+ * x [rows, K] with row stride ldx elements, out [N, K]; MEAN is the floor division upstream
+ * applies to integer tensors; MIN/MAX report the lowest edge position among equal values.
+ */
+int gno_segment_reduce_int(const gno_csr* g, const void* x, int64_t ldx,
+                           void* out, int64_t ldo, int64_t* arg,
+                           int64_t arg_fill, int64_t K, int elem_bytes,
+                           int reduce, int accumulate, gno_stream_t stream);
+
+/*
  * Last-dim form: out[b, i] = reduce_{k in row i} x[b, gidx[k]] for x [B, L]
  * (dim == last, 1-D index): index_select / index_add_ along dim 1
  * (benchmark_native_index_add_.py:62, benchmark_fused_*_reduce.py dim=1).

@@ -82,7 +82,12 @@ def run_c1(iters):
     ms_cold = timeit(lambda: (gno_b200.clear_caches(), gno_b200.scatter(src, idx, 0, None, N, "sum")), iters, True)
     ms = timeit(lambda: gno_b200.scatter(src, idx, 0, None, N, "sum"), iters, True)
     ab = E * (F * 4 + 8) + N * F * 4  # int64 index as given
-    emit("C1 scatter_sum fp32 [1M,64]->100k (plan cached)", ms, E, "edges", ab, l2="flushed")
+    ix = idx.view(-1, 1).expand(E, F)
+    nat = timeit(lambda: torch.zeros(N, F, device=DEV).scatter_add_(0, ix, src), iters, True)
+    nat_max = timeit(lambda: torch.zeros(N, F, device=DEV).scatter_reduce_(0, ix, src, "amax", include_self=False), iters, True)
+    emit("C1 scatter_sum fp32 [1M,64]->100k (plan cached)", ms, E, "edges", ab, l2="flushed",
+         native_torch_ms={"zeros+scatter_add_ (what torch_scatter.scatter_sum runs)": round(nat, 4),
+                          "zeros+scatter_reduce_(amax)": round(nat_max, 4)})
     emit("C1 scatter_sum fp32 [1M,64]->100k (cold: plan build included)", ms_cold, E, "edges", ab, l2="flushed")
     for red in ("mean", "max", "min", "mul"):
         ms = timeit(lambda: gno_b200.scatter(src, idx, 0, None, N, red, return_arg=True), iters, True)
@@ -95,9 +100,13 @@ def run_c1(iters):
     for red in ("sum", "max", "mean"):
         for dim in (0, 1):
             ms = timeit(lambda: gno_b200.scatter(s16, ifull, dim, None, L, red, return_arg=True), iters)
+            natred = {"sum": "sum", "max": "amax", "mean": "mean"}[red]
+            nat = timeit(lambda: torch.zeros(L, L, device=DEV, dtype=torch.float16).scatter_reduce_(
+                dim, ifull, s16, natred, include_self=False), iters)
             emit(f"script-shape scatter_{red} fp16 ({L},{L}) full-shape index dim{dim}", ms, L * L, "elems",
                  L * L * (2 + 8) + L * L * 2, a100_ref_ms={"sum": (6.688, 3.678), "max": (14.531, 6.704),
-                                                            "mean": (13.602, 7.616)}[red][dim])
+                                                            "mean": (13.602, 7.616)}[red][dim],
+                 native_torch_ms={f"zeros+scatter_reduce_({natred})": round(nat, 4)})
 
 
 def graph(name):
@@ -111,7 +120,9 @@ def graph(name):
 def run_c2(iters):
     n, e, F, src, dst, x = graph("products")
     t = timeit(lambda: planmod.build_plan(dst, n), 5)
-    emit("C2 plan build (dst radix sort + rowptr + lists), 61.9M edges", t, e, "edges", e * (8 + 4 + 4) + n * 8)
+    nat = timeit(lambda: torch.sort(dst, stable=True), 3)
+    emit("C2 plan build (dst radix sort + rowptr + lists), 61.9M edges", t, e, "edges", e * (8 + 4 + 4) + n * 8,
+         native_torch_ms={"torch.sort(dst, stable=True) alone (CUB, int64 keys)": round(nat, 3)})
     plan = planmod.build_plan(dst, n)
     gidx = plan.sorted_ids(src)
     out = torch.empty(n, F, device=DEV)
@@ -119,7 +130,13 @@ def run_c2(iters):
         arg = red == "max"
         ms = timeit(lambda: gno_b200.segment_reduce(plan, x, red, gidx=gidx, eid=plan.perm, want_arg=arg,
                                                     out=None if arg else out), iters)
-        emit(f"C2 products gather->scatter_{red} fp32 F=100", ms, e, "edges", agg_bytes(n, e, F, 4, arg))
+        extra = {}
+        if red == "sum":
+            def native():
+                o = torch.zeros(n, F, device=DEV)
+                o.index_add_(0, dst, x.index_select(0, src))   # materialises the [E, F] messages (24.7 GB)
+            extra["native_torch_ms"] = {"index_select + zeros + index_add_ (unfused)": round(timeit(native, 3), 3)}
+        emit(f"C2 products gather->scatter_{red} fp32 F=100", ms, e, "edges", agg_bytes(n, e, F, 4, arg), **extra)
 
 
 def run_c3(iters):
@@ -155,7 +172,14 @@ def run_c4(iters):
     col = plan.sorted_ids(src).to(torch.int64)
     val = torch.rand(e, device=DEV, generator=g)
     ms = timeit(lambda: gno_b200.spmm_csr(rowptr, col, val, X, "sum"), iters)
-    emit("C4 spmm CSR (reddit-shaped, F=256 fp32, plan cached)", ms, e, "nnz", agg_bytes(n, e, F, 4, weight=True))
+    try:
+        csr = torch.sparse_csr_tensor(rowptr, col, val, (n, n))
+        nat = round(timeit(lambda: torch.sparse.mm(csr, X), 3), 3)
+        del csr
+    except Exception as ex:
+        nat = repr(ex)[:100]
+    emit("C4 spmm CSR (reddit-shaped, F=256 fp32, plan cached)", ms, e, "nnz", agg_bytes(n, e, F, 4, weight=True),
+         native_torch_ms={"torch.sparse.mm(csr, X) (cuSPARSE)": nat})
     # coalesced COO of the graph, then transpose / coalesce
     index = torch.stack([plan.erow.to(torch.int64), col])
     del plan
@@ -171,8 +195,13 @@ def run_c4(iters):
     dup_v = torch.cat([cv, cv])
     del perm
     ms = timeit(lambda: gno_b200.coalesce(dup_i, dup_v, n, n), max(3, iters // 2))
+    try:
+        nat = round(timeit(lambda: torch.sparse_coo_tensor(dup_i, dup_v, (n, n)).coalesce(), 3), 3)
+    except Exception as ex:
+        nat = repr(ex)[:100]
     emit(f"C4 coalesce of 2x duplicated, permuted COO ({2 * nnz} entries)", ms, 2 * nnz, "nnz",
-         (16 + 4) * 2 * nnz + (16 + 4) * nnz, passes="5 x 8-bit over 36 key bits (64-bit keys)")
+         (16 + 4) * 2 * nnz + (16 + 4) * nnz, passes="5 x 8-bit over 36 key bits (64-bit keys)",
+         native_torch_ms={"sparse_coo_tensor(...).coalesce()": nat})
 
 
 def run_sort(iters):
@@ -180,15 +209,21 @@ def run_sort(iters):
     n = 1 << 28
     x = torch.rand(n, device=DEV, generator=g)
     ms = timeit(lambda: gno_b200.sort(x), max(3, iters // 2))
-    emit(f"sort fp32 1-D {n} (values + int64 indices, stable)", ms, n, "keys", n * (4 + 4 + 8), passes="4 x 8-bit")
+    nat = timeit(lambda: torch.sort(x, stable=True), 3)
+    emit(f"sort fp32 1-D {n} (values + int64 indices, stable)", ms, n, "keys", n * (4 + 4 + 8), passes="4 x 8-bit",
+         native_torch_ms={"torch.sort(stable=True) (CUB)": round(nat, 3)})
     y = torch.rand(20000, 20000, device=DEV, generator=g)
     for dim in (0, 1):
         ms = timeit(lambda: gno_b200.sort(y, dim), max(3, iters // 2))
-        emit(f"sort fp32 (20000,20000) dim{dim}", ms, y.numel(), "keys", y.numel() * 16, passes="6 x 8-bit (47-bit key)")
+        nat = timeit(lambda: torch.sort(y, dim=dim, stable=True), 3)
+        emit(f"sort fp32 (20000,20000) dim{dim}", ms, y.numel(), "keys", y.numel() * 16, passes="6 x 8-bit (47-bit key)",
+             native_torch_ms={"torch.sort(stable=True)": round(nat, 3)})
     k = torch.randint(0, 1 << 31, (n,), device=DEV, generator=g, dtype=torch.int64).to(torch.int32)
     v = torch.arange(n, device=DEV, dtype=torch.int32)
     ms = timeit(lambda: gno_b200.sort_pairs(k, v), max(3, iters // 2))
-    emit(f"sort_pairs u32 keys + u32 payload, {n}", ms, n, "keys", n * 16, passes="4 x 8-bit")
+    nat = timeit(lambda: torch.sort(k, stable=True), 3)
+    emit(f"sort_pairs u32 keys + u32 payload, {n}", ms, n, "keys", n * 16, passes="4 x 8-bit",
+         native_torch_ms={"torch.sort(int32 keys, stable=True): values + int64 indices (CUB)": round(nat, 3)})
 
 
 def run_c5(iters):

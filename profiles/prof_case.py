@@ -28,6 +28,15 @@ if case == "c5":
     dst, src = ids_r >> 3, ids_c
     x = torch.randn(n_src, F, device=DEV, generator=g).to(torch.bfloat16)
     n = n_dst
+elif case == "rmat26":   # bench.py's default workload at N=1: the full graph
+    n, e, F, dtype = B.workload_shape("rmat26")
+    src, dst = B.rmat_edges(26, e, DEV, 42)
+    x = B.feature_block(0, 1, n, F, dtype, DEV)
+elif case == "c4spmm":   # C4: CSR spmm with edge values on the Reddit-shaped graph, F=256 fp32
+    n, e, _, _, ex, off = B.WORKLOADS["reddit"]
+    F = 256
+    src, dst = B.make_graph(n, n, e, ex, off, DEV, 42)
+    x = torch.randn(n, F, device=DEV, generator=g)
 elif case in ("reddit_bf16", "reddit", "products"):
     n, e, F, dtype, ex, off = B.WORKLOADS[case]
     src, dst = B.make_graph(n, n, e, ex, off, DEV, 42)
@@ -39,9 +48,11 @@ elif case == "c1":
     x = torch.rand(e, F, device=DEV, generator=g)
 plan = planmod.build_plan(dst, n)
 gidx = plan.sorted_ids(src)
+del src, dst
 arg = red in ("max", "min")
+w = torch.rand(plan.E, device=DEV, generator=g) if case == "c4spmm" else None
 torch.cuda.synchronize()
 for _ in range(reps):
-    gno_b200.segment_reduce(plan, x, red, gidx=gidx, eid=plan.perm, want_arg=arg)
+    gno_b200.segment_reduce(plan, x, red, gidx=gidx, eid=plan.perm, want_arg=arg, weights=w)
 torch.cuda.synchronize()
 print("done", case, red, plan.chunk_len, plan.n_span, plan.n_empty)

@@ -75,7 +75,7 @@ def main():
         fracs = [float(v) for v in parts[2].split(",")] if len(parts) > 2 and parts[2] else None
         split = parts[3] if len(parts) > 3 and parts[3] else "dest"
         own = parts[4] if len(parts) > 4 and parts[4] else "cyclic"
-        pblocks = int(parts[5]) if len(parts) > 5 and parts[5] else 296
+        pblocks = int(parts[5]) if len(parts) > 5 and parts[5] else 148
         gno_b200.clear_caches()
         torch.cuda.empty_cache()
         t0 = time.perf_counter()
@@ -107,7 +107,7 @@ def main():
         xonly = timed((lambda: agg.exchange_push(x_local)) if mode == "push" else
                       (lambda: agg.exchange_needed(x_local, recv)), args.steps)
 
-        ronly = timed(lambda: agg.reduce_stages(recv, "sum", out), args.steps)
+        ronly = timed(lambda: agg.reduce_stages(recv, "sum", out, x_local=x_local), args.steps)
         info = torch.tensor([agg.n_needed, agg.n_needed - agg.recv_splits[rank], src.numel()], device=dev,
                             dtype=torch.float64)
         mx = info.clone()

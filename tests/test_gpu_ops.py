@@ -788,3 +788,59 @@ def test_gather_csr_nd(cuda):
     with pytest.raises(ValueError):
         gno_b200.spmm_csr(torch.tensor([0, 2, 3]).to(cuda), torch.zeros(5, dtype=torch.long).to(cuda), None,
                           torch.ones(4, 2).to(cuda))
+
+
+# ---- integer values (PyG's bookkeeping calls) ----------------------------------------------------
+def test_scatter_integer_values(cuda):
+    """TopKPooling / to_dense_batch: scatter_add(batch.new_ones(n), batch, dim=0) on int64
+    (graph_benchmark/models/ptg_models.py:165-172 -> GraphUNet), plus every integer reduce against a
+    sequential restatement (mean = floor division, arg = lowest position among ties)."""
+    import torch_scatter
+    g = torch.Generator().manual_seed(41)
+    batch = torch.sort(torch.randint(0, 13, (5000,), generator=g)).values
+    ones = batch.new_ones(batch.numel())
+    got = torch_scatter.scatter_add(ones.to(cuda), batch.to(cuda), dim=0)
+    assert got.dtype == torch.int64 and torch.equal(got.cpu(), torch.bincount(batch))
+    # large magnitudes: exact where an fp32 round trip would not be
+    big = torch.randint(-(1 << 40), 1 << 40, (3000,), generator=g)
+    idx = torch.randint(0, 7, (3000,), generator=g)
+    want = torch.zeros(7, dtype=torch.int64).index_add_(0, idx, big)
+    assert torch.equal(torch_scatter.scatter_add(big.to(cuda), idx.to(cuda), dim=0, dim_size=7).cpu(), want)
+    for dtype in (torch.int32, torch.int64):
+        E, K, N = 700, 5, 11
+        src = torch.randint(-9, 10, (E, K), generator=g).to(dtype)
+        idx = torch.randint(0, N - 2, (E,), generator=g)
+        for red in ("sum", "mean", "min", "max", "mul"):
+            s = src.clamp(-2, 2) if red == "mul" else src
+            r = getattr(torch_scatter, "scatter_" + red)(s.to(cuda), idx.to(cuda), 0, None, N)
+            want = torch.zeros(N, K, dtype=torch.int64)
+            warg = torch.full((N, K), E, dtype=torch.int64)
+            for i in range(N):
+                rows = torch.nonzero(idx == i).flatten()
+                if rows.numel() == 0:
+                    want[i] = 1 if red == "mul" else 0
+                    continue
+                v = s[rows].long()
+                if red == "sum":
+                    want[i] = v.sum(0)
+                elif red == "mean":
+                    want[i] = torch.div(v.sum(0), rows.numel(), rounding_mode="floor")
+                elif red == "mul":
+                    want[i] = v.prod(0)
+                else:
+                    m = v.max(0).values if red == "max" else v.min(0).values
+                    want[i] = m
+                    warg[i] = rows[(v == m.unsqueeze(0)).float().argmax(0)]
+            if red in ("min", "max"):
+                assert r[0].dtype == dtype and torch.equal(r[0].cpu().long(), want), (dtype, red)
+                assert torch.equal(r[1].cpu(), warg), (dtype, red)
+            else:
+                assert r.dtype == dtype and torch.equal(r.cpu().long(), want), (dtype, red)
+    # broadcast along the last dim (B > 1, K == 1) and bool / uint8 inputs
+    src = torch.randint(0, 5, (4, 300), generator=g)
+    idx = torch.randint(0, 9, (300,), generator=g)
+    want = torch.zeros(4, 9, dtype=torch.int64).index_add_(1, idx, src)
+    assert torch.equal(torch_scatter.scatter_add(src.to(cuda), idx.to(cuda), dim=1, dim_size=9).cpu(), want)
+    mask = torch.rand(300, generator=g) > 0.5
+    assert torch.equal(torch_scatter.scatter_add(mask.to(cuda), idx.to(cuda), dim=0, dim_size=9).cpu(),
+                       torch.zeros(9, dtype=torch.int64).index_add_(0, idx, mask.long()))
