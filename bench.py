@@ -462,10 +462,23 @@ def run_rmat(args):
     agg = None
     stages = 1
     if world > 1:
-        stages = args.stages if args.stages > 0 else 4
+        # measured (profiles/scaling/r2h_*, r2k_*): at N=2 the rank's own half of the sources hides the
+        # whole exchange (2 stages: 22.5 ms vs 24.8 unstaged); at N=4 own rows, then the most-referenced
+        # quarter of the remote rows, then the rest: 13.2 ms vs 16.3
         fracs = [float(v) for v in args.stage_fracs.split(",")] if args.stage_fracs else None
-        if fracs is not None and len(fracs) != stages:
-            raise SystemExit("--stage-fracs needs one share per stage")
+        if args.stages > 0:
+            stages = args.stages
+        elif args.split == "source":
+            stages = 2 if world <= 2 else 3
+            if fracs is None and stages == 3:
+                fracs = [0.25, 0.75]
+        elif args.split == "hybrid":
+            stages = 2 if world <= 2 else 5
+        else:
+            stages = 4
+        n_fr = stages - 1 if args.split in ("source", "hybrid") else stages
+        if fracs is not None and len(fracs) != n_fr:
+            raise SystemExit(f"--stage-fracs needs {n_fr} shares for {stages} {args.split} stages")
         own = args.ownership if args.ownership != "auto" else ("xorfold" if world & (world - 1) == 0 else "cyclic")
         kw = dict(rank=rank, world=world, cyclic_rows=N, stages=stages, stage_fracs=fracs,
                   row_weight=args.row_weight, split=args.split, ownership=own, push_blocks=args.push_blocks)
@@ -980,7 +993,7 @@ def main():
     ap.add_argument("--stage-fracs", default="",
                     help="rmat workloads: comma-separated shares of the stages (dest split: cost share of each "
                          "destination sub-range; source split: share of the remote rows in each remote stage)")
-    ap.add_argument("--split", default="source", choices=["source", "dest"],
+    ap.add_argument("--split", default="source", choices=["source", "dest", "hybrid"],
                     help="rmat workloads at N>1: pipeline the exchange over groups of SOURCE rows (own rows, "
                          "then remote rows by decreasing reference count; stages accumulate) or over "
                          "DESTINATION sub-ranges (every row written once)")

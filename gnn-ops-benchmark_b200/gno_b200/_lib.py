@@ -79,6 +79,9 @@ PROTOTYPES = {
     "gno_scatter_elementwise": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                         c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_size_t,
                                         c_void_p]),
+    "gno_scatter_planned_ok": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int]),
+    "gno_scatter_planned": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
+                                    c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "gno_coalesce_workspace": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int,
                                        POINTER(c_size_t)]),
     "gno_coalesce": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64,

@@ -147,8 +147,8 @@ class DistAggregator:
             # needed-rows exchanges pipeline over DESTINATION sub-ranges (see _setup_needed)
             self.xstages, stages = max(1, int(stages)), 1
             self.stage_fracs, self.row_weight = stage_fracs, int(row_weight)
-            if split not in ("dest", "source"):
-                raise ValueError("split must be 'dest' or 'source'")
+            if split not in ("dest", "source", "hybrid"):
+                raise ValueError("split must be 'dest', 'source' or 'hybrid'")
             self.split = split if self.xstages > 1 else "dest"
         self.stages = max(1, min(int(stages), max(self.max_rows, 1)))
         # single-stage layout: row of the padded gather buffer [P * max_rows, F]
@@ -227,6 +227,22 @@ class DistAggregator:
             self.sub_bounds = None
             self.stage_of_edge = first[inv]
             self.src_local = local       # stage 0 gathers this rank's own rows straight from x_local
+        elif K > 1 and self.split == "hybrid":
+            # stage 0 = the edges whose source this rank owns (read from x_local, nothing to wait
+            # for); the remote-source edges are cut by DESTINATION sub-range into stages 1..K-1, each
+            # accumulating onto stage 0's result: one extra pass over the output in total, instead of
+            # one per stage as in the source split, and every sub-range waits only for the remote
+            # rows it reads first
+            remote_e = owner != self.rank
+            counts = torch.bincount(self.dst_local[remote_e], minlength=self.n_out) + self.row_weight
+            self.sub_bounds = stage_ranges(counts, K - 1, self.stage_fracs).cpu()
+            sb = self.sub_bounds.to(dev)
+            dstage = torch.searchsorted(sb[1:].contiguous(), self.dst_local, right=True).clamp_(max=K - 2)
+            stage_e = torch.where(remote_e, dstage + 1, torch.zeros_like(dstage))
+            first = torch.full((n_u,), K - 1, dtype=torch.int64, device=dev)
+            first.scatter_reduce_(0, inv, stage_e, "amin", include_self=True)
+            self.stage_of_edge = stage_e
+            self.src_local = local
         elif K > 1:
             counts = torch.bincount(self.dst_local, minlength=self.n_out) + self.row_weight
             self.sub_bounds = stage_ranges(counts, K, self.stage_fracs).cpu()
@@ -345,12 +361,12 @@ class DistAggregator:
         peer needs for its stage s once from local HBM and stores it into that peer's buffer.
         max_blocks caps its grid when it runs beside the reduction (0 = fill the chip)."""
         from ._lib import check, lib
-        from .plan import _ptr, _stream
+        from .plan import _on_device, _ptr, _stream
         t, hdl, ptrs, stages = st
         seg_c, off_c, seg = stages[s]
         rows = self._stage_serve(s)
         F, es = x_local.size(1), x_local.element_size()
-        with torch.cuda.device(x_local.device):
+        with _on_device(x_local.device):
             check(lib.gno_push_rows(_ptr(x_local), F * es, x_local.stride(0) * es, _ptr(rows),
                                     rows.numel(), self.world, ptrs, seg_c, off_c, F * es,
                                     seg[(self.rank + 1) % self.world], int(max_blocks),
@@ -377,7 +393,7 @@ class DistAggregator:
         import ctypes
         import torch.distributed._symmetric_memory as symm
         from ._lib import check, lib
-        from .plan import _ptr, _stream
+        from .plan import _on_device, _ptr, _stream
         if x_local.size(0) != self.n_local:
             raise ValueError("x_local must hold this rank's rows")
         x_local = x_local.contiguous()
@@ -393,7 +409,7 @@ class DistAggregator:
             st = self._ag_bufs[key] = (t, hdl, ptrs, seg, off)
         t, hdl, ptrs, seg, off = st
         hdl.barrier(channel=0)
-        with torch.cuda.device(x_local.device):
+        with _on_device(x_local.device):
             check(lib.gno_push_rows(_ptr(x_local), F * es, x_local.stride(0) * es, None,
                                     self.world * self.n_local, self.world, ptrs, seg, off, F * es,
                                     ((self.rank + 1) % self.world) * self.n_local, 0,
@@ -473,12 +489,14 @@ class DistAggregator:
                     self._stage_plans.append((p, gidx, p.perm, 0, self.n_out, False))
                     continue
                 where = torch.nonzero(self.stage_of_edge == s).flatten()
-                if self.split == "source":
+                if self.split == "source" or (self.split == "hybrid" and s == 0):
                     lo, hi, acc = 0, self.n_out, s > 0
+                elif self.split == "hybrid":
+                    lo, hi, acc = int(self.sub_bounds[s - 1]), int(self.sub_bounds[s]), True
                 else:
                     lo, hi, acc = int(self.sub_bounds[s]), int(self.sub_bounds[s + 1]), False
                 p = planmod.build_plan(self.dst_local[where] - lo, hi - lo)
-                own = self.split == "source" and s == 0   # rows of x_local, not of the receive buffer
+                own = self.split in ("source", "hybrid") and s == 0   # rows of x_local, not of the receive buffer
                 gidx = p.sorted_ids((self.src_local if own else self.src_needed)[where])
                 eid = p.sorted_ids(where)
                 self._stage_plans.append((p, gidx, eid, lo, hi, acc))
@@ -490,7 +508,7 @@ class DistAggregator:
         nothing).  Also what bench.py times as the kernel-only loop."""
         from . import ops
         cur = torch.cuda.current_stream(recv.device)
-        own0 = self.split == "source" and self.xstages > 1
+        own0 = self.split in ("source", "hybrid") and self.xstages > 1
         if own0 and x_local is None:
             raise ValueError("split='source' reduces stage 0 from x_local")
         for s, (p, gidx, eid, lo, hi, acc) in enumerate(self.xstage_plans()):
@@ -524,9 +542,9 @@ class DistAggregator:
         self.xstage_plans()
         x_local = x_local.contiguous()
         kred = reduce
-        if self.split == "source":
+        if self.split in ("source", "hybrid"):
             if reduce not in ("sum", "mean") or want_arg:
-                raise NotImplementedError("split='source' accumulates across stages: sum / mean only "
+                raise NotImplementedError(f"split='{self.split}' accumulates across stages: sum / mean only "
                                           "(use split='dest' for min / max / mul)")
             kred = "sum"
         if out is None:
@@ -548,7 +566,7 @@ class DistAggregator:
             recv = x_full if x_full is not None else torch.empty((self.n_needed, F), dtype=x_local.dtype, device=dev)
         # split="source": stage 0 holds only rows this rank owns; the reduction gathers them straight
         # from x_local, so stage 0 has no exchange at all (and nothing to wait for)
-        local0 = self.split == "source"
+        local0 = self.split in ("source", "hybrid")
         self._mark("step start", cur)
         with torch.cuda.stream(ps):
             if push:
@@ -566,7 +584,7 @@ class DistAggregator:
                     self.exchange_needed(x_local, recv, stage=s)
                 ev[s].record(ps)
         self.reduce_stages(recv, kred, out, want_arg, arg, events=ev, x_local=x_local)
-        if reduce == "mean" and self.split == "source":
+        if reduce == "mean" and self.split in ("source", "hybrid"):
             if self._row_counts is None:
                 self._row_counts = torch.bincount(self.dst_local, minlength=self.n_out).clamp_(min=1)
             out.div_(self._row_counts.to(out.dtype).view(-1, 1))

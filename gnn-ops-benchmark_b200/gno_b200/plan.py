@@ -17,14 +17,37 @@ from ._lib import check, gno_csr, lib
 
 def default_chunk_len(num_edges):
     """Edges per worker chunk: large enough that chunk-boundary partials are ~1 % of the
-    traffic, small enough that small inputs still fill 148 SMs."""
-    if num_edges >= (1 << 23):
+    traffic, small enough that small inputs still fill 148 SMs.  Thresholds from
+    profiles/c1_chunk.py on a B200 (F=64 fp32, L2 flushed): 250 k edges 27.6 / 33.8 / 44.2 us at
+    32 / 64 / 128; 1 M edges 78.8 / 72.7 / 68.6 / 85.0 us at 32 / 64 / 128 / 256; 4 M edges
+    226 / 220 / 212 us at 64 / 128 / 256."""
+    if num_edges >= 3_000_000:
         return 256
-    if num_edges >= (1 << 21):
+    if num_edges >= 750_000:
         return 128
-    if num_edges >= (1 << 19):
+    if num_edges >= 400_000:
         return 64
     return 32
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def _on_device(device):
+    """`with torch.cuda.device(d)` only when d is not already current: the context manager costs
+    several microseconds per call (two driver round trips), which is what the reference scripts'
+    timeit loops see on small inputs."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(device)
 
 
 def _ptr(t):
@@ -90,7 +113,7 @@ class CSRPlan:
             nbytes = ctypes.c_size_t()
             check(lib.gno_plan_lists_workspace(self.N, ctypes.byref(nbytes)))
             ws = _workspace(nbytes.value, dev)
-            with torch.cuda.device(dev):
+            with _on_device(dev):
                 check(lib.gno_plan_lists(_ptr(self.rowptr), self.N, self.chunk_len,
                                          _ptr(self.srow) if self.n_span else None,
                                          _ptr(self.zrow) if self.n_empty else None,
@@ -116,7 +139,7 @@ def build_plan(index, num_rows, chunk_len=None):
     nbytes = ctypes.c_size_t()
     check(lib.gno_plan_workspace(E, N, ctypes.byref(nbytes)))
     ws = _workspace(nbytes.value, dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         check(lib.gno_plan_build(_ptr(index), E, N, p.chunk_len, _ptr(p.rowptr), _ptr(p.perm),
                                  _ptr(p.erow), _ptr(info), _ptr(ws), ws.numel(), _stream(dev)))
     p._finish(info)
@@ -136,7 +159,7 @@ def plan_from_rowptr(rowptr, nnz, chunk_len=None):
     p.rowptr, p.perm = rowptr, None
     p.erow = torch.empty(max(E, 1), dtype=torch.int32, device=dev)[:E]
     info = torch.empty(4, dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         check(lib.gno_plan_from_rowptr(_ptr(rowptr), N, E, p.chunk_len, _ptr(p.erow), _ptr(info),
                                        _stream(dev)))
     p._finish(info)
@@ -165,6 +188,10 @@ class PlanCache:
             return p
         self.misses += 1
         p = build_plan(index, num_rows, chunk_len)
+        if p.n_dropped:
+            import warnings
+            warnings.warn(f"gno_b200: {p.n_dropped} index entries outside [0, {int(num_rows)}) were dropped "
+                          "(upstream torch_scatter leaves this undefined on CUDA)", RuntimeWarning, stacklevel=3)
         p._keepalive = index  # the key is a raw pointer: keep the tensor alive
         self._d[key] = p
         while len(self._d) > self.capacity:

@@ -282,6 +282,26 @@ int gno_scatter_elementwise(const void* src, const int64_t* index, int64_t B,
                             int64_t N, int dtype, int reduce, int accumulate,
                             void* ws, size_t ws_bytes, gno_stream_t stream);
 
+/*
+ * The same op on a cached plan of the index (atomic-free, deterministic for
+ * every dtype): the host sorts the index once (gno_sort_pairs on the flat
+ * output position of every element, stable) into
+ *   order [B*E*K]   int32  position e along the scatter dim of the j-th element
+ *                          in OUTPUT order
+ *   ptr   [B*N*K+1] int32  output element o = (b*N+n)*K+k owns order[ptr[o]:ptr[o+1])
+ * and reuses it for every call on that index tensor (the reference scripts time
+ * 100 calls on one index, op_bm_scripts/benchmark_scatter_add.py:97-118).  A CTA
+ * stages up to 16 adjacent source columns in shared memory and reduces each
+ * output's segment sequentially (ascending e: upstream's CPU loop order; ties
+ * of MIN/MAX keep the lowest position).  gno_scatter_planned_ok says whether a
+ * source column fits in shared memory.
+ */
+int gno_scatter_planned_ok(int64_t B, int64_t E, int64_t K, int64_t N, int dtype);
+int gno_scatter_planned(const void* src, const int32_t* order, const int32_t* ptr,
+                        int64_t B, int64_t E, int64_t K, void* out, int64_t* arg,
+                        int64_t N, int dtype, int reduce, int accumulate,
+                        gno_stream_t stream);
+
 /* ------------------------------------------------- coalesce / transpose -- */
 /*
  * torch_sparse.coalesce(index, value, m, n, op): sort COO entries by

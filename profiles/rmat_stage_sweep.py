@@ -66,8 +66,10 @@ def main():
         dist.barrier()
         torch.cuda.synchronize()
         t = torch.tensor([a.elapsed_time(b) / steps], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
+        every = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        timed.per_rank = [round(float(v), 3) for v in every]
+        return max(timed.per_rank)
 
     for setting in args.settings.split(";"):
         parts = setting.split(":")
@@ -108,6 +110,10 @@ def main():
                       (lambda: agg.exchange_needed(x_local, recv)), args.steps)
 
         ronly = timed(lambda: agg.reduce_stages(recv, "sum", out, x_local=x_local), args.steps)
+        ronly_ranks = timed.per_rank
+        rows_edges = torch.tensor([float(hi - lo), float(src.numel())], device=dev, dtype=torch.float64)
+        allre = [torch.empty_like(rows_edges) for _ in range(world)]
+        dist.all_gather(allre, rows_edges)
         info = torch.tensor([agg.n_needed, agg.n_needed - agg.recv_splits[rank], src.numel()], device=dev,
                             dtype=torch.float64)
         mx = info.clone()
@@ -116,6 +122,8 @@ def main():
             print(json.dumps({"workload": args.workload, "n_gpus": world, "exchange": mode, "stages": K, "split": split, "ownership": own, "push_blocks": pblocks,
                               "stage_fracs": fracs, "stage_edges_rank0": [p.E for p, *_ in plans], "step_ms": round(step_ms, 3),
                               "exchange_only_ms": round(xonly, 3), "reduce_only_ms": round(ronly, 3),
+                              "reduce_only_ms_per_rank": ronly_ranks,
+                              "rows_per_rank": [int(v[0]) for v in allre], "edges_per_rank": [int(v[1]) for v in allre],
                               "edges_per_s": E / (step_ms * 1e-3),
                               "recv_rows_max": int(mx[0]), "remote_rows_max": int(mx[1]),
                               "remote_GB_max": round(float(mx[1]) * F * 2 / 1e9, 3), "edges_max": int(mx[2]),

@@ -124,6 +124,25 @@ def _worker(rank, world, port, N, E, F, ret):
                         if refs.numel():
                             refs_prev = int(refs.min())
             ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
+        # hybrid split: stage 0 = own-source edges over all rows; the remote-source edges by destination
+        # sub-range, each stage after the rows it reads first have arrived
+        aggh = DistAggregator(bounds, s_r, d_r, exchange="needed", cyclic_rows=N, stages=4, stage_fracs=[0.2, 0.3, 0.5],
+                              split="hybrid", row_weight=2)
+        recv = aggh.exchange_needed(x[rank::world].contiguous(), gather_rows=lambda t, r: t.index_select(0, r))
+        own_edge = (s_r % world) == rank
+        ok &= bool((aggh.stage_of_edge[own_edge] == 0).all()) and bool((aggh.stage_of_edge[~own_edge] >= 1).all())
+        ok &= aggh.recv_cnt[0][1 - rank] == 0
+        got = torch.zeros(hi - lo, F)
+        for s in range(4):
+            m = aggh.stage_of_edge == s
+            if s >= 1:
+                a, b = int(aggh.sub_bounds[s - 1]), int(aggh.sub_bounds[s])
+                ok &= bool(((d_r[m] >= a) & (d_r[m] < b)).all())
+                if m.any():
+                    ok &= int(aggh.src_needed[m].max()) < aggh.stage_row0[s + 1]
+                    ok &= int(aggh.src_needed[m].min()) >= aggh.stage_row0[1]
+            got += oracle.gather_scatter(recv, aggh.src_needed[m], d_r[m], hi - lo, "sum")[0]
+        ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
         # xorfold ownership (balanced on ids with skewed bits): pad the feature rows to an even count
         from gno_b200.dist import xorfold_global_ids
         xp = torch.cat([x, torch.zeros(N % 2, F)])

@@ -89,9 +89,11 @@ def _worker(rank, world, port, ret):
                 ok &= torch.allclose(got.cpu(), wsum[lo:hi], rtol=1e-5, atol=1e-3)
         # source split (own rows first, then remote rows by decreasing reference count; stages accumulate)
         wmean, _ = oracle.gather_scatter(x, src, dst, N, "mean")
-        for mode, K, fr in (("push", 2, None), ("push", 4, [0.1, 0.3, 0.6]), ("needed", 3, [0.2, 0.8])):
+        for mode, K, fr, split in (("push", 2, None, "source"), ("push", 4, [0.1, 0.3, 0.6], "source"),
+                                   ("needed", 3, [0.2, 0.8], "source"), ("push", 4, [0.2, 0.3, 0.5], "hybrid"),
+                                   ("push", 2, None, "hybrid"), ("needed", 3, None, "hybrid")):
             aggs = DistAggregator(bounds, shards[rank][0].to(dev), shards[rank][1].to(dev), exchange=mode,
-                                  cyclic_rows=N, stages=K, stage_fracs=fr, split="source")
+                                  cyclic_rows=N, stages=K, stage_fracs=fr, split=split, row_weight=2)
             xl = x[rank::world].contiguous().to(dev)
             for _ in range(3):
                 ok &= torch.allclose(aggs.aggregate(xl, "sum").cpu(), wsum[lo:hi], rtol=1e-5, atol=1e-3)
@@ -150,10 +152,11 @@ def _worker_world1(rank, world, port, ret):
                 ok &= torch.equal(gm.float().cpu(), wmax)
                 ok &= torch.equal(ga.cpu(), warg)
         # source split on one rank: every row is this rank's own, the remote stages are empty
-        agg = DistAggregator(bounds, src.to(dev), dst.to(dev), rank=0, world=1, exchange="push", cyclic_rows=N,
-                             stages=3, stage_fracs=[0.1, 0.9], split="source")
-        for _ in range(2):
-            ok &= torch.allclose(agg.aggregate(x.to(dev), "sum").float().cpu(), wsum, rtol=1e-2, atol=1e-2)
+        for split in ("source", "hybrid"):
+            agg = DistAggregator(bounds, src.to(dev), dst.to(dev), rank=0, world=1, exchange="push", cyclic_rows=N,
+                                 stages=3, stage_fracs=[0.1, 0.9], split=split)
+            for _ in range(2):
+                ok &= torch.allclose(agg.aggregate(x.to(dev), "sum").float().cpu(), wsum, rtol=1e-2, atol=1e-2)
         ret[0] = bool(ok)
     finally:
         dist.destroy_process_group()

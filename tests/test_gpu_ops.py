@@ -444,8 +444,11 @@ def test_sparse_tensor(cuda):
     ei = torch.stack([torch.randint(0, m, (nnz,), generator=g), torch.randint(0, n, (nnz,), generator=g)])
     val = torch.rand(nnz, generator=g)
     x = torch.randn(n, F, generator=g)
-    A = SparseTensor.from_edge_index(ei.to(cuda), val.to(cuda), sparse_sizes=(m, n))
     ci, cv = oracle.coalesce(ei, val, m, n)
+    # unique entries in random order (SparseTensor sorts, and — like upstream — never merges
+    # duplicates: test_sparse_tensor_keeps_duplicate_edges covers those)
+    shuffle = torch.randperm(ci.size(1), generator=g)
+    A = SparseTensor.from_edge_index(ci[:, shuffle].to(cuda), cv[shuffle].to(cuda), sparse_sizes=(m, n))
     dense = torch.zeros(m, n)
     dense[ci[0], ci[1]] = cv
     assert A.nnz() == ci.size(1)
@@ -844,3 +847,118 @@ def test_scatter_integer_values(cuda):
     mask = torch.rand(300, generator=g) > 0.5
     assert torch.equal(torch_scatter.scatter_add(mask.to(cuda), idx.to(cuda), dim=0, dim_size=9).cpu(),
                        torch.zeros(9, dtype=torch.int64).index_add_(0, idx, mask.long()))
+
+
+# ---- full-shape index on the cached plan (second call onwards): atomic-free path ----------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape,dim,N", [((223, 223), 0, 223), ((223, 223), 1, 56), ((300, 40), 0, 37),
+                                         ((5, 40, 7), 1, 9), ((3, 1000), 1, 11), ((2000, 3), 0, 2100)])
+def test_scatter_full_shape_planned_path(cuda, dtype, shape, dim, N):
+    import gno_b200
+    from gno_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape) + dim)
+    src = ((torch.rand(*shape, generator=g) * 32).round() / 32 - 0.25).to(dtype)
+    src.view(-1)[::97] = float("nan")
+    src.view(-1)[5::131] = 0.0
+    src.view(-1)[6::131] = -0.0
+    idx = torch.randint(0, N, shape, generator=g)
+    idx.view(-1)[::53] = N + 3          # out of range: dropped
+    s_d, i_d = src.to(cuda), idx.to(cuda)
+    view = torch.int16 if dtype != torch.float32 else torch.int32
+    for red in ("sum", "mean", "mul", "min", "max"):
+        s_use = s_d if red != "mul" else (s_d.nan_to_num(1.0) * 0.25 + 0.875)
+        s_cpu = s_use.cpu()
+        want, warg = oracle.scatter(s_cpu, idx, dim, N, red)      # drops out-of-range destinations too
+        first = gno_b200.scatter(s_use, i_d, dim, None, N, red, return_arg=True)
+        second = gno_b200.scatter(s_use, i_d, dim, None, N, red, return_arg=True)
+        assert any(k[0] == "fs_plan" for k in ops._memo_store), "the second call must run on the cached plan"
+        for got in (first, second):
+            if red in ("min", "max"):
+                assert torch.equal(got[0].cpu().view(view), want.view(view)), red
+                assert torch.equal(got[1].cpu(), warg), red
+            else:
+                a, b = got.float().cpu(), want.float()
+                assert torch.equal(torch.isnan(a), torch.isnan(b)), red
+                ok = ~torch.isnan(b)
+                fin = torch.where(torch.isnan(s_cpu.float()), torch.zeros(()), s_cpu.float().abs())
+                scale = oracle.scatter(fin, idx, dim, N, "sum" if red != "mul" else "mul")[0]
+                assert not ((a - b).abs()[ok] > TOL[dtype] * torch.maximum(scale, b.abs())[ok] + 1e-30).any(), red
+    # out= forms on the planned path
+    out0 = ((torch.rand(want_shape(shape, dim, N), generator=g) * 8).round() / 8).to(dtype)
+    clean = torch.nan_to_num(s_d, nan=0.5)
+    for red in ("sum", "max"):
+        o = out0.clone().to(cuda)
+        got = gno_b200.scatter(clean, i_d, dim, o, None, red, return_arg=True)
+        fresh, farg = oracle.scatter(clean.cpu(), idx, dim, N, red)
+        if red == "sum":
+            mag = oracle.scatter(clean.cpu().float().abs(), idx, dim, N, "sum")[0]
+            close(got, (out0.float() + fresh.float()).to(dtype), dtype, out0.float().abs() + mag)
+        else:
+            w, wa = _ref_minmax_with_out(fresh, farg, out0, shape[dim], "max")
+            assert torch.equal(got[0].cpu(), w) and torch.equal(got[1].cpu(), wa)
+
+
+def want_shape(shape, dim, N):
+    s = list(shape)
+    s[dim] = N
+    return s
+
+
+# ---- more edges than a plan indexes (>= 2^31): slices along the scatter dim, combined in order --
+@pytest.mark.parametrize("dim", [0, 1])
+def test_scatter_sliced_beyond_plan_limit(cuda, dim, monkeypatch):
+    """benchmark_scatter_multiply.py:52-58 sweeps a 2.4 G-element 1-D tensor; plans index edges with
+    32 bits, so longer inputs go through slices.  The slicing logic is exercised with a small limit
+    (test_gpu_fullsize has the real 2^31-element case)."""
+    import gno_b200
+    from gno_b200 import ops
+    monkeypatch.setattr(ops, "_MAX_PLAN_EDGES", 700)
+    g = torch.Generator().manual_seed(77)
+    E, K, N = 2500, 6, 23
+    src = (torch.randn(E, K, generator=g) * 4).round() / 4
+    idx = torch.randint(0, N - 2, (E,), generator=g)
+    idx[::97] = N + 1
+    if dim == 1:
+        src = src.t().contiguous()
+    for red in ("sum", "mean", "mul", "max", "min"):
+        s = src if red != "mul" else torch.where(src.abs() > 2, torch.full_like(src, 2.0), torch.full_like(src, -1.0))
+        got = gno_b200.scatter(s.to(cuda), idx.to(cuda), dim, None, N, red, return_arg=True)
+        want, warg = oracle.scatter(s, idx, dim, N, red)
+        if red in ("max", "min"):
+            assert torch.equal(got[0].cpu(), want) and torch.equal(got[1].cpu(), warg), red
+        elif red == "mul":
+            assert torch.equal(got.cpu(), want)
+        else:
+            assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-4), red
+    ones = torch.ones(E, dtype=torch.int64)
+    got = gno_b200.scatter(ones.to(cuda), idx.to(cuda), 0, None, N, "sum")
+    assert torch.equal(got.cpu(), torch.bincount(idx[idx < N], minlength=N))
+
+
+def test_scatter_prepared_launch_cache(cuda):
+    """Repeated full-shape calls on one index reuse a prepared launch (what the reference scripts'
+    timeit loops do): later calls must track a NEW src tensor, a changed index (version bump) and
+    different reduces independently."""
+    import gno_b200
+    from gno_b200 import ops
+    gno_b200.clear_caches()
+    g = torch.Generator().manual_seed(5)
+    L, N = 150, 40
+    idx = torch.randint(0, N, (L, L), generator=g)
+    i_d = idx.to(cuda)
+    for rep in range(4):
+        src = (torch.randn(L, L, generator=g) * 8).round() / 8
+        for red in ("sum", "max"):
+            got = gno_b200.scatter(src.to(cuda), i_d, 0, None, N, red, return_arg=True)
+            want, warg = oracle.scatter(src, idx, 0, N, red)
+            if red == "max":
+                assert torch.equal(got[0].cpu(), want) and torch.equal(got[1].cpu(), warg), rep
+            else:
+                assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-4), rep
+    assert len(ops._fast_calls) >= 2
+    i_d[0, 0] = (i_d[0, 0] + 1) % N           # in-place edit: version bump invalidates plan and launch
+    idx[0, 0] = (idx[0, 0] + 1) % N
+    src = (torch.randn(L, L, generator=g) * 8).round() / 8
+    for _ in range(3):
+        got = gno_b200.scatter(src.to(cuda), i_d, 0, None, N, "sum")
+        assert torch.allclose(got.cpu(), oracle.scatter(src, idx, 0, N, "sum")[0], rtol=1e-5, atol=1e-4)
