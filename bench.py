@@ -462,10 +462,15 @@ def run_rmat(args):
     agg = None
     stages = 1
     if world > 1:
-        # measured (profiles/scaling/r2h_*, r2k_*): at N=2 the rank's own half of the sources hides the
-        # whole exchange (2 stages: 22.5 ms vs 24.8 unstaged); at N=4 own rows, then the most-referenced
-        # quarter of the remote rows, then the rest: 13.2 ms vs 16.3
+        # Stage structure of the overlapped exchange, measured on 2 / 4 / 8 B200s
+        # (profiles/scaling/r2h_*, r2k_*, r2p_*, r2q_*): N=2 — own-source edges first, they hide the
+        # whole exchange (22.1 ms vs 24.8 unstaged); N=4 — own-source edges, then the remote-source
+        # edges in two destination halves (12.9 ms vs 13.2 for the source split, 16.3 unstaged);
+        # N=8 — own rows, the most-referenced quarter of the remote rows, the rest (7.8 ms vs 8.9
+        # hybrid, 10.1 unstaged)
         fracs = [float(v) for v in args.stage_fracs.split(",")] if args.stage_fracs else None
+        if args.split == "auto":
+            args.split = "hybrid" if 2 < world <= 4 else "source"
         if args.stages > 0:
             stages = args.stages
         elif args.split == "source":
@@ -473,7 +478,7 @@ def run_rmat(args):
             if fracs is None and stages == 3:
                 fracs = [0.25, 0.75]
         elif args.split == "hybrid":
-            stages = 2 if world <= 2 else 5
+            stages = 2 if world <= 2 else 3
         else:
             stages = 4
         n_fr = stages - 1 if args.split in ("source", "hybrid") else stages
@@ -606,6 +611,7 @@ def run_rmat(args):
               "empty_rows_rank0": plans[0][0].n_empty if len(plans) == 1 else None,
               "chunk_len": plans[0][0].chunk_len,
               "exchange": args.exchange if world > 1 else None, "stages": stages if world > 1 else None,
+              "stage_fracs": fracs if world > 1 else None,
               "split": args.split if world > 1 else None,
               "stage_edges_rank0": [p.E for p, *_ in plans] if world > 1 else None,
               "stage_recv_rows_rank0": ([agg.stage_row0[s + 1] - agg.stage_row0[s] for s in range(stages)]
@@ -993,10 +999,11 @@ def main():
     ap.add_argument("--stage-fracs", default="",
                     help="rmat workloads: comma-separated shares of the stages (dest split: cost share of each "
                          "destination sub-range; source split: share of the remote rows in each remote stage)")
-    ap.add_argument("--split", default="source", choices=["source", "dest", "hybrid"],
+    ap.add_argument("--split", default="auto", choices=["auto", "source", "dest", "hybrid"],
                     help="rmat workloads at N>1: pipeline the exchange over groups of SOURCE rows (own rows, "
-                         "then remote rows by decreasing reference count; stages accumulate) or over "
-                         "DESTINATION sub-ranges (every row written once)")
+                         "then remote rows by decreasing reference count; stages accumulate), over DESTINATION "
+                         "sub-ranges (every row written once), or hybrid (own-source edges, then the "
+                         "remote-source edges by destination sub-range); auto = the measured best per N")
     ap.add_argument("--ownership", default="auto", choices=["auto", "cyclic", "xorfold"],
                     help="rmat workloads at N>1: feature row i lives on rank i %% N (cyclic) or on the XOR of "
                          "the log2(N)-bit groups of i (xorfold: balanced on R-MAT ids, whose bits are skewed); "

@@ -148,13 +148,14 @@ __global__ void __launch_bounds__(256) push_rows_kernel(const PushParams p) {
 // of 10.3 (profiles/scaling/r2g_*).
 constexpr int kTmaStages = 4;
 constexpr int kTmaAhead = 2;            // chunks of gathers in flight ahead of the chunk being stored
-constexpr int kTmaChunkBytes = 16384;
+constexpr int kTmaChunkMax = 16384;  // ring slot size upper bound (GNO_PUSH_CHUNK picks 4096..16384)
 
 struct PushTmaParams {
   PushParams b;
   int64_t chunk0[kMaxPeers + 1];  // chunk0[q] = first chunk of requester q (chunks never straddle requesters)
   int64_t start_chunk;            // rotation, so the ranks store to different receivers at any moment
   int rows_per_chunk;
+  int chunk_bytes;                // ring slot size
 };
 
 __global__ void __launch_bounds__(32) push_rows_tma_kernel(const PushTmaParams p) {
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(32) push_rows_tma_kernel(const PushTmaParams p
       locate(it, q, slot0, rows);
       if (lane == 0) mbar_expect_tx(bar + st, (uint32_t)rows * rb);
       __syncwarp();
-      unsigned char* dst = buf + (size_t)st * kTmaChunkBytes;
+      unsigned char* dst = buf + (size_t)st * p.chunk_bytes;
       for (int r = lane; r < rows; r += 32) {
         const int64_t row = p.b.serve_rows[slot0 + r];
         bulk_g2s(dst + (size_t)r * rb, p.b.x + row * p.b.src_stride, rb, bar + st);
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(32) push_rows_tma_kernel(const PushTmaParams p
         int64_t slot0;
         locate(j, q, slot0, rows);
         char* out = p.b.peer_buf[q] + (p.b.row_off[q] + (slot0 - p.b.seg[q])) * p.b.dst_stride;
-        bulk_s2g(out, buf + (size_t)st * kTmaChunkBytes, (uint32_t)rows * rb);
+        bulk_s2g(out, buf + (size_t)st * p.chunk_bytes, (uint32_t)rows * rb);
         bulk_commit();
       }
     }
@@ -364,10 +365,14 @@ int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes, co
   // the chip the LDG/STG form is faster: 4.4 vs 6.2 ms for RMAT-26's exchange at P=2, where half of
   // the rows are local copies that move at HBM speed)
   if (tma_env && max_blocks > 0 && serve_rows != nullptr && a % 16 == 0 && dst_stride_bytes == row_bytes &&
-      row_bytes <= kTmaChunkBytes / 4) {
+      row_bytes <= 4096 / 4) {
+    // ring slot size: 8 KB x 4 slots = 32 KB per CTA, two CTAs (two issuing warps) per SM by default
+    static const int chunk_env = getenv("GNO_PUSH_CHUNK") ? atoi(getenv("GNO_PUSH_CHUNK")) : 8192;
+    const int chunk_bytes = chunk_env < 4096 ? 4096 : (chunk_env > kTmaChunkMax ? kTmaChunkMax : chunk_env / 16 * 16);
     PushTmaParams t;
     t.b = p;
-    t.rows_per_chunk = (int)(kTmaChunkBytes / row_bytes);
+    t.chunk_bytes = chunk_bytes;
+    t.rows_per_chunk = (int)(chunk_bytes / row_bytes);
     t.chunk0[0] = 0;
     for (int q = 0; q < n_peers; ++q)
       t.chunk0[q + 1] = t.chunk0[q] + ceil_div(seg[q + 1] - seg[q], (int64_t)t.rows_per_chunk);
@@ -376,10 +381,11 @@ int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes, co
     int q0 = 0;
     while (q0 + 1 < n_peers && p.start >= seg[q0 + 1]) ++q0;
     t.start_chunk = n_chunks > 0 ? t.chunk0[q0] % n_chunks : 0;
-    const size_t smem = 128 + (size_t)kTmaStages * kTmaChunkBytes;
+    const size_t smem = 128 + (size_t)kTmaStages * chunk_bytes;
     static bool attr_set = false;
     if (!attr_set) {
-      GNO_CUDA(cudaFuncSetAttribute(push_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GNO_CUDA(cudaFuncSetAttribute(push_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    128 + kTmaStages * kTmaChunkMax));
       attr_set = true;
     }
     // one warp per SM drives 617 GB/s, two 677 GB/s (profiles/scaling/r2h_push_micro_tma.txt);
