@@ -416,6 +416,8 @@ def per_config(iters):
         for line in bench_ops.RESULTS:
             res[line["op"]] = {"ms": line["ms"], "algorithmic_GB": line["algorithmic_GB"],
                                "frac_of_peak": line["frac_of_peak"]}
+            if "frac_dram" in line:   # real DRAM traffic (ncu capture of the same launch) over the time measured here
+                res[line["op"]]["frac_dram"] = line["frac_dram"]
     gno_b200.clear_caches()
     torch.cuda.empty_cache()
     return res
@@ -666,7 +668,9 @@ def run_rmat(args):
                 "data": "synthetic", "config": config_of(args.workload), "detail": detail, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": launches, "parity": parity,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "frac": achieved / peak, "traffic": traffic,
+                             "dram_frac": (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                             "peak_source": peak_src,
                              "kernel": "segreduce_staged_kernel + segfinish_kernel (rank 0's shard)",
                              "kernel_ms": k_ms, "algorithmic_bytes": abytes}}
         if cpu is not None:
@@ -950,7 +954,9 @@ def run_weak(args):
                                           else f"NCCL, {args.stages}-stage exchange")) if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "parity": parity,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "dram_frac": (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "peak_source": peak_src,
                          "kernel": "segreduce_staged_kernel (+ segfinish_kernel)", "kernel_ms": k_ms,
                          "algorithmic_bytes": abytes},
         }

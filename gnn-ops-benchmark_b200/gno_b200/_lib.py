@@ -79,6 +79,8 @@ PROTOTYPES = {
     "gno_scatter_elementwise": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                         c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_size_t,
                                         c_void_p]),
+    "gno_scatter_planned_layout": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int, POINTER(c_int),
+                                           POINTER(c_int)]),
     "gno_scatter_planned_ok": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int]),
     "gno_scatter_planned": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                     c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
@@ -102,7 +104,7 @@ def _load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.gno_abi_version() != 2:
+    if lib.gno_abi_version() != 3:
         raise GnoError("libgno_b200.so ABI version mismatch")
     return lib
 

@@ -363,12 +363,17 @@ _FS_PLAN = os.environ.get("GNO_FS_PLAN", "1") != "0"
 
 
 def _full_shape_plan(index, dim, N, B, E, K, dt):
-    """(order, ptr) of a full-shape index, or None.  The first call on an index tensor takes the
-    one-launch atomic path (no preparation); from the second call on — the reference scripts'
-    timeit loops, a GNN layer reusing its graph — the index is sorted once into a plan cached on
-    the tensor's identity + version, and every later call is atomic-free."""
-    if not _FS_PLAN or B * E * K == 0 or not lib.gno_scatter_planned_ok(B, E, K, N, dt):
+    """(order, ptr) of a full-shape index in the blocked layout of gno_scatter_planned
+    (include/gno_b200.h), or None.  The first call on an index tensor takes the one-launch atomic
+    path (no preparation); from the second call on — the reference scripts' timeit loops, a GNN
+    layer reusing its graph — the index is sorted once into a plan cached on the tensor's
+    identity + version, and every later call is atomic-free."""
+    if not _FS_PLAN or B * E * K == 0:
         return None
+    kb_c, ob_c = ctypes.c_int(), ctypes.c_int()
+    if not lib.gno_scatter_planned_layout(B, E, K, N, dt, ctypes.byref(kb_c), ctypes.byref(ob_c)):
+        return None
+    kb, order_bytes = kb_c.value, ob_c.value
     seen = _memo("fs_seen", index, (dim, N), lambda: [0])
     seen[0] += 1
     if seen[0] < 2:
@@ -376,18 +381,21 @@ def _full_shape_plan(index, dim, N, B, E, K, dt):
 
     def build():
         dev = index.device
-        total = B * N * K
+        ncb = (K + (1 << kb) - 1) >> kb
+        total = (B * ncb * N) << kb
         idx3 = index.view(B, E, K)
-        o = (torch.arange(B, device=dev).view(B, 1, 1) * N + idx3) * K + torch.arange(K, device=dev).view(1, 1, K)
+        k = torch.arange(K, device=dev)
+        blk = (torch.arange(B, device=dev).view(B, 1, 1) * ncb + (k >> kb).view(1, 1, K)) * N   # (b*ncb + cb)*N
+        o = ((blk + idx3) << kb) + (k & ((1 << kb) - 1)).view(1, 1, K)
         o = torch.where((idx3 >= 0) & (idx3 < N), o, torch.full_like(o, total)).reshape(-1)
         iota = torch.arange(o.numel(), dtype=torch.int32, device=dev)
         skey, perm = sort_pairs(o, iota, 0, max(1, int(total).bit_length()))
-        order = (torch.div(perm, K, rounding_mode="floor") % E).to(torch.int32)
+        order = (torch.div(perm, K, rounding_mode="floor") % E).to(torch.int16 if order_bytes == 2 else torch.int32)
         ptr = torch.zeros(total + 1, dtype=torch.int64, device=dev)
         counts = torch.bincount(o[o < total], minlength=total)
         torch.cumsum(counts, 0, out=ptr[1:])
         return order.contiguous(), ptr.to(torch.int32)
-    return _memo("fs_plan", index, (dim, N), build)
+    return _memo("fs_plan", index, (dim, N, kb, order_bytes), build)
 
 
 def _scatter_int(src, idx1d, dim, out, accumulate, N, B, E, K, out_shape, reduce, red, want_arg):

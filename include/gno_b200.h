@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GNO_ABI_VERSION 2
+#define GNO_ABI_VERSION 3
 
 typedef void* gno_stream_t; /* a cudaStream_t */
 
@@ -284,20 +284,27 @@ int gno_scatter_elementwise(const void* src, const int64_t* index, int64_t B,
 
 /*
  * The same op on a cached plan of the index (atomic-free, deterministic for
- * every dtype): the host sorts the index once (gno_sort_pairs on the flat
- * output position of every element, stable) into
- *   order [B*E*K]   int32  position e along the scatter dim of the j-th element
- *                          in OUTPUT order
- *   ptr   [B*N*K+1] int32  output element o = (b*N+n)*K+k owns order[ptr[o]:ptr[o+1])
- * and reuses it for every call on that index tensor (the reference scripts time
- * 100 calls on one index, op_bm_scripts/benchmark_scatter_add.py:97-118).  A CTA
- * stages up to 16 adjacent source columns in shared memory and reduces each
- * output's segment sequentially (ascending e: upstream's CPU loop order; ties
- * of MIN/MAX keep the lowest position).  gno_scatter_planned_ok says whether a
- * source column fits in shared memory.
+ * every dtype): the host sorts the index once (gno_sort_pairs, stable) and
+ * reuses the plan for every call on that index tensor (the reference scripts
+ * time 100 calls on one index, op_bm_scripts/benchmark_scatter_add.py:97-118).
+ * The plan is BLOCKED by the CTA that consumes it: a CTA owns KB = 1 << kb_shift
+ * adjacent columns (gno_scatter_planned_layout), ncb = ceil(K / KB), and the
+ * blocked id of output (b, n, k = cb*KB + kk) is
+ *   ob = (((b*ncb + cb)*N + n) << kb_shift) + kk
+ *   ptr   [B*ncb*N*KB + 1] int32  output ob owns order[ptr[ob]:ptr[ob+1])
+ *   order [B*E*K] int16 (order_bytes = 2, E <= 32768) or int32: position e along
+ *         the scatter dim of each element, elements in ascending (ob, e)
+ * so every CTA reads one contiguous slice of each.  It stages its KB source
+ * columns in shared memory and reduces each output's segment sequentially
+ * (ascending e: upstream's CPU loop order; ties of MIN/MAX keep the lowest
+ * position).  gno_scatter_planned_layout returns 1 and the layout parameters
+ * when a source column fits in shared memory and the plan indexes with 32 bits,
+ * else 0 (gno_scatter_planned_ok: the same test without the outputs).
  */
+int gno_scatter_planned_layout(int64_t B, int64_t E, int64_t K, int64_t N, int dtype,
+                               int* kb_shift, int* order_bytes);
 int gno_scatter_planned_ok(int64_t B, int64_t E, int64_t K, int64_t N, int dtype);
-int gno_scatter_planned(const void* src, const int32_t* order, const int32_t* ptr,
+int gno_scatter_planned(const void* src, const void* order, const int32_t* ptr,
                         int64_t B, int64_t E, int64_t K, void* out, int64_t* arg,
                         int64_t N, int dtype, int reduce, int accumulate,
                         gno_stream_t stream);

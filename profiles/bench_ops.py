@@ -58,11 +58,26 @@ def timeit(fn, iters, flush=False):
 RESULTS = []  # every emitted line, for callers that run this in-process (bench.py per_config)
 
 
-def emit(name, ms, units, unit_name, abytes, **extra):
+try:
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as _f:
+        _TRAFFIC = json.load(_f).get("detail", {})
+except OSError:
+    _TRAFFIC = {}
+
+
+def emit(name, ms, units, unit_name, abytes, dram_key=None, **extra):
+    """dram_key: entry of profiles/traffic.json (ncu dram__bytes of the same launch) — frac_dram is
+    the share of the measured copy peak the kernel's REAL DRAM traffic reaches in the time measured
+    here; frac_of_peak is on algorithmic bytes and exceeds 1 where L2 serves repeated gathers."""
     gbs = abytes / (ms * 1e-3) / 1e9
     line = {"op": name, "ms": round(ms, 4), unit_name + "_per_s": units / (ms * 1e-3),
             "algorithmic_GB": round(abytes / 1e9, 3), "achieved_GBps": round(gbs, 1),
             "frac_of_peak": round(gbs / PEAK, 4), "peak_GBps": PEAK, "peak_source": PEAK_SRC}
+    t = _TRAFFIC.get(dram_key) if dram_key else None
+    if t:
+        line["dram_GB_ncu"] = round(t["dram_bytes"] / 1e9, 3)
+        line["frac_dram"] = round(t["dram_bytes"] / (ms * 1e-3) / 1e9 / PEAK, 4)
+        line["l2_hit_pct_ncu"] = t["l2_hit_pct"].get("segreduce_staged_kernel")
     line.update(extra)
     RESULTS.append(line)
     print(json.dumps(line), flush=True)
@@ -85,7 +100,7 @@ def run_c1(iters):
     ix = idx.view(-1, 1).expand(E, F)
     nat = timeit(lambda: torch.zeros(N, F, device=DEV).scatter_add_(0, ix, src), iters, True)
     nat_max = timeit(lambda: torch.zeros(N, F, device=DEV).scatter_reduce_(0, ix, src, "amax", include_self=False), iters, True)
-    emit("C1 scatter_sum fp32 [1M,64]->100k (plan cached)", ms, E, "edges", ab, l2="flushed",
+    emit("C1 scatter_sum fp32 [1M,64]->100k (plan cached)", ms, E, "edges", ab, dram_key="c1_sum", l2="flushed",
          native_torch_ms={"zeros+scatter_add_ (what torch_scatter.scatter_sum runs)": round(nat, 4),
                           "zeros+scatter_reduce_(amax)": round(nat_max, 4)})
     emit("C1 scatter_sum fp32 [1M,64]->100k (cold: plan build included)", ms_cold, E, "edges", ab, l2="flushed")
@@ -136,7 +151,8 @@ def run_c2(iters):
                 o = torch.zeros(n, F, device=DEV)
                 o.index_add_(0, dst, x.index_select(0, src))   # materialises the [E, F] messages (24.7 GB)
             extra["native_torch_ms"] = {"index_select + zeros + index_add_ (unfused)": round(timeit(native, 3), 3)}
-        emit(f"C2 products gather->scatter_{red} fp32 F=100", ms, e, "edges", agg_bytes(n, e, F, 4, arg), **extra)
+        emit(f"C2 products gather->scatter_{red} fp32 F=100", ms, e, "edges", agg_bytes(n, e, F, 4, arg),
+             dram_key="products_sum" if red == "sum" else None, **extra)
 
 
 def run_c3(iters):
@@ -151,7 +167,8 @@ def run_c3(iters):
             arg = red in ("max", "min")
             ms = timeit(lambda: gno_b200.segment_reduce(plan, xs, red, gidx=gidx, eid=plan.perm, want_arg=arg), iters)
             emit(f"C3 reddit gather->scatter_{red}{'+arg' if arg else ''} {str(dtype)[6:]} F=602", ms, e, "edges",
-                 agg_bytes(n, e, F, es, arg))
+                 agg_bytes(n, e, F, es, arg),
+                 dram_key=("reddit" if dtype == torch.float32 else "reddit_bf16") + "_" + red)
     # un-fused scatter_max(src[E', 602]) at E' = E/8 (full src would be 276 GB)
     e8 = e // 8
     g = torch.Generator(device=DEV).manual_seed(3)
@@ -179,6 +196,7 @@ def run_c4(iters):
     except Exception as ex:
         nat = repr(ex)[:100]
     emit("C4 spmm CSR (reddit-shaped, F=256 fp32, plan cached)", ms, e, "nnz", agg_bytes(n, e, F, 4, weight=True),
+         dram_key="c4spmm_sum",
          native_torch_ms={"torch.sparse.mm(csr, X) (cuSPARSE)": nat})
     # coalesced COO of the graph, then transpose / coalesce
     index = torch.stack([plan.erow.to(torch.int64), col])
@@ -250,7 +268,7 @@ def run_c5(iters):
     del dst, src
     ms = timeit(lambda: gno_b200.segment_reduce(plan, x, "sum", gidx=gidx), iters)
     emit("C5 per-GPU slice (P=8): RMAT-26 shard, 2^27 edges -> 2^23 rows, F=128 bf16", ms, e, "edges",
-         agg_bytes(n_dst, e, F, 2), max_row_len=plan.max_len, empty_rows=plan.n_empty)
+         agg_bytes(n_dst, e, F, 2), dram_key="c5_sum", max_row_len=plan.max_len, empty_rows=plan.n_empty)
 
 
 RUNS = {"c1": run_c1, "c2": run_c2, "c3": run_c3, "c4": run_c4, "sort": run_sort, "c5": run_c5}

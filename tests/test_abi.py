@@ -31,7 +31,7 @@ def test_header_symbols_exported():
 def test_abi_argument_validation_without_gpu():
     from gno_b200 import _lib
     lib = _lib.lib
-    assert lib.gno_abi_version() == 2
+    assert lib.gno_abi_version() == 3
     n = ctypes.c_size_t()
     assert lib.gno_sort_pairs_workspace(1000, 4, 4, ctypes.byref(n)) == 0 and n.value > 8000
     assert lib.gno_sort_pairs_workspace(1000, 3, 4, ctypes.byref(n)) == 1  # GNO_ERR_INVALID
