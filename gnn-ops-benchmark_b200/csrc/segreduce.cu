@@ -693,37 +693,46 @@ __global__ void __launch_bounds__(256) segfinish_kernel(const SegParams p) {
   // this kernel's launch latency overlap the tail of the main kernel.
   const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t tstride = (int64_t)gridDim.x * blockDim.x;
-  for (int phase = 0; phase < 2; ++phase) {
+  if (fill16 && !p.accumulate) {
+    // Empty-row fill, warp-centric: one coalesced load brings 32 row ids, then the warp issues
+    // per_empty independent 512-byte stores (the ids travel by shuffle).  The earlier forms — one
+    // id load per 16-byte store, then four — waited on a DRAM-latency load for every 64 bytes
+    // stored: 2.9 TB/s on RMAT-26's 40 M empty rows, 29 % of the stall samples on that load
+    // (profiles/r3b_finish_rmat26_ncu.txt).
+    const float fv = finalize<T, RED>(red_init<T, RED>(), kNoArg, 0.f, false, 1.f, 0, p.arg_fill, nullptr);
+    Words<16> o;
+#pragma unroll
+    for (int q = 0; q < EPV16; ++q) set_elem<T, 16>(o, q, fv);
+    const int lane = threadIdx.x & 31;
+    const int pe = (int)per_empty;
+    const int q32 = 32 / pe, r32 = 32 % pe;
+    const int64_t wstride = tstride;           // 32 rows per warp per round
+    for (int64_t base = tid0 - lane; base < p.n_empty; base += wstride) {
+      const int64_t mine = base + lane < p.n_empty ? (int64_t)__ldg(p.zrow + base + lane) : -1;
+      int r = lane / pe, c = lane - r * pe;
+      for (int k = 0; k < pe; ++k) {   // item t = lane + 32 k of the 32 * pe pieces: the same trip count in every lane
+        const int64_t row = __shfl_sync(0xffffffffu, mine, r);
+        if (row >= 0) {
+          st_vec<16>(static_cast<char*>(p.out) + row * p.ldo_bytes + (int64_t)c * 16, o);
+          if constexpr (ARG) {
+            if (p.arg) {
+              longlong2* ap = reinterpret_cast<longlong2*>(p.arg + row * p.F + (int64_t)c * EPV16);
+#pragma unroll
+              for (int q = 0; q < EPV16 / 2; ++q) ap[q] = make_longlong2(p.arg_fill, p.arg_fill);
+            }
+          }
+        }
+        c += r32;
+        r += q32;
+        if (c >= pe) { c -= pe; ++r; }
+      }
+    }
+  }
+  for (int phase = (fill16 ? 1 : 0); phase < 2; ++phase) {
   if (phase == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
   const int64_t i_begin = phase == 0 ? n_a + tid0 : tid0;
   const int64_t i_end = phase == 0 ? total : n_a;
   for (int64_t i = i_begin; i < i_end; i += tstride) {
-    if (i >= n_a && fill16) {
-      const int64_t j = i - n_a;
-      int64_t z, c;
-      if (total < (int64_t(1) << 31)) {  // 32-bit division when it fits
-        z = (unsigned)j / (unsigned)per_empty;
-        c = (unsigned)j - (unsigned)z * (unsigned)per_empty;
-      } else {
-        z = j / per_empty;
-        c = j - z * per_empty;
-      }
-      const int64_t row = p.zrow[z];
-      // the reduction's identity through finalize: 0 (sum/mean/min/max), 1 (mul)
-      const float fv = finalize<T, RED>(red_init<T, RED>(), kNoArg, 0.f, false, 1.f, 0, p.arg_fill, nullptr);
-      Words<16> o;
-#pragma unroll
-      for (int q = 0; q < EPV16; ++q) set_elem<T, 16>(o, q, fv);
-      st_vec<16>(static_cast<char*>(p.out) + row * p.ldo_bytes + c * 16, o);
-      if constexpr (ARG) {
-        if (p.arg) {
-          longlong2* ap = reinterpret_cast<longlong2*>(p.arg + row * p.F + c * EPV16);
-#pragma unroll
-          for (int q = 0; q < EPV16 / 2; ++q) ap[q] = make_longlong2(p.arg_fill, p.arg_fill);
-        }
-      }
-      continue;
-    }
     float a[4];
     int e[4];
     int64_t row, f0;
