@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256) push_rows_kernel(const PushParams p) {
 constexpr int kTmaStages = 4;
 constexpr int kTmaAhead = 2;            // chunks of gathers in flight ahead of the chunk being stored
 constexpr int kTmaChunkMax = 16384;  // ring slot size upper bound (GNO_PUSH_CHUNK picks 4096..16384)
+static std::atomic<int> g_push_chunk{0};   // gno_push_set_chunk; 0 = GNO_PUSH_CHUNK / default
 
 struct PushTmaParams {
   PushParams b;
@@ -330,6 +331,13 @@ int gno_pad_rows(const void* src, int64_t rows, int64_t row_bytes, int64_t src_s
   return GNO_OK;
 }
 
+int gno_push_set_chunk(int bytes) {
+  GNO_CHECK_ARG(bytes == 0 || (bytes >= 4096 && bytes <= gno::kTmaChunkMax),
+                "gno_push_set_chunk: %d outside {0, 4096..16384}", bytes);
+  gno::g_push_chunk.store(bytes, std::memory_order_relaxed);
+  return GNO_OK;
+}
+
 int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes, const int64_t* serve_rows,
                   int64_t n_serve, int n_peers, void* const* peer_bufs, const int64_t* seg,
                   const int64_t* row_off, int64_t dst_stride_bytes, int64_t start_slot,
@@ -367,8 +375,14 @@ int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes, co
   if (tma_env && max_blocks > 0 && serve_rows != nullptr && a % 16 == 0 && dst_stride_bytes == row_bytes &&
       row_bytes <= 4096 / 4) {
     // ring slot size: 8 KB x 4 slots = 32 KB per CTA, two CTAs (two issuing warps) per SM by default
+    // (gno_push_set_chunk, else GNO_PUSH_CHUNK, else 8 KB.  Measured on RMAT-26, profiles/scaling/r3f_*,
+    // r3h_*: where the reduction beside the push is the critical path — 4 GPUs — the light 8 KB ring
+    // wins, 12.75 vs 13.09 ms; where the exchange is — 8 GPUs — the 16 KB ring, twice the bytes in
+    // flight under HBM contention, wins 7.70 vs 8.22 ms)
     static const int chunk_env = getenv("GNO_PUSH_CHUNK") ? atoi(getenv("GNO_PUSH_CHUNK")) : 8192;
-    const int chunk_bytes = chunk_env < 4096 ? 4096 : (chunk_env > kTmaChunkMax ? kTmaChunkMax : chunk_env / 16 * 16);
+    const int chunk_req = g_push_chunk.load(std::memory_order_relaxed) > 0 ? g_push_chunk.load(std::memory_order_relaxed)
+                                                                             : chunk_env;
+    const int chunk_bytes = chunk_req < 4096 ? 4096 : (chunk_req > kTmaChunkMax ? kTmaChunkMax : chunk_req / 16 * 16);
     PushTmaParams t;
     t.b = p;
     t.chunk_bytes = chunk_bytes;

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "gno_pad_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "gno_push_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, POINTER(c_void_p),
                               POINTER(c_int64), POINTER(c_int64), c_int64, c_int64, c_int, c_void_p]),
+    "gno_push_set_chunk": (c_int, [c_int]),
     "gno_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p,
                                 c_void_p]),
     "gno_scatter_elementwise_workspace": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int, c_int,

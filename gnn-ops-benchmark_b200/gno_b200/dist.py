@@ -107,7 +107,7 @@ class DistAggregator:
 
     def __init__(self, bounds, src_global, dst_local, rank=None, world=None, group=None, stages=1,
                  feature_bounds=None, exchange="allgather", cyclic_rows=None, stage_fracs=None,
-                 row_weight=0, split="dest", ownership="cyclic", push_blocks=148):
+                 row_weight=0, split="dest", ownership="cyclic", push_blocks=148, push_chunk=0):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -147,8 +147,21 @@ class DistAggregator:
             # needed-rows exchanges pipeline over DESTINATION sub-ranges (see _setup_needed)
             self.xstages, stages = max(1, int(stages)), 1
             self.stage_fracs, self.row_weight = stage_fracs, int(row_weight)
+            # "mixed[D]" (e.g. "mixed16"): the RECEIVER decides — a rank whose rows average at least D edges (default
+            # 16) splits by source (its few rows make the accumulate passes cheap and its short
+            # own-source stage needs remote rows early), a rank of many low-degree rows takes the
+            # hybrid (one extra pass over its output instead of one per stage; its long own-source
+            # stage hides the first, large push).  Owners only serve request lists, so ranks may mix;
+            # only the number of stages (barriers) is common.
+            if split.startswith("mixed"):
+                deg = float(split[5:]) if len(split) > 5 else 16.0
+                mine = src_global.numel() / max(self.n_out, 1)
+                split = "source" if mine >= deg else "hybrid"
+                if split == "hybrid":
+                    stage_fracs = None      # stage_fracs describes the source ranks' remote groups
+                    self.stage_fracs = None
             if split not in ("dest", "source", "hybrid"):
-                raise ValueError("split must be 'dest', 'source' or 'hybrid'")
+                raise ValueError("split must be 'dest', 'source', 'hybrid' or 'mixed[min_degree]'")
             self.split = split if self.xstages > 1 else "dest"
         self.stages = max(1, min(int(stages), max(self.max_rows, 1)))
         # single-stage layout: row of the padded gather buffer [P * max_rows, F]
@@ -170,6 +183,9 @@ class DistAggregator:
         self._push_events = None
         self._row_counts = None
         self.push_blocks = int(push_blocks)
+        if push_chunk:      # ring slot bytes of the TMA push (process-wide; 0 keeps the library default)
+            from ._lib import check, lib
+            check(lib.gno_push_set_chunk(int(push_chunk)))
         self.trace = None   # set to [] to collect (label, cuda event) pairs of one staged step
         self.exchange_mode = exchange
         if exchange in ("needed", "push"):

@@ -251,6 +251,10 @@ int gno_gather_rows(const void* x, int64_t x_rows, int64_t row_bytes,
  * provides the cross-rank barrier (new work, no reference counterpart: the
  * reference is single-GPU).
  */
+/* Ring slot size of the TMA-staged form of gno_push_rows (4096..16384 bytes, four slots per
+ * CTA; 0 = the GNO_PUSH_CHUNK environment variable, else 8192): small slots leave shared memory to
+ * a reduction running beside the push, large ones keep more bytes in flight. */
+int gno_push_set_chunk(int bytes);
 int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes,
                   const int64_t* serve_rows, int64_t n_serve, int n_peers,
                   void* const* peer_bufs, const int64_t* seg,
