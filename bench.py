@@ -465,27 +465,37 @@ def run_rmat(args):
     stages = 1
     if world > 1:
         # Stage structure of the overlapped exchange, measured on 2 / 4 / 8 B200s
-        # (profiles/scaling/r2h_*, r3d_* ... r3h_*; per-rank timelines in the same files).  Every N
-        # splits by SOURCE: own-source edges first (nothing to wait for), then the most-referenced
-        # remote rows, then the rest.  N=2: two stages, the own half hides the whole exchange.
-        # N=4: the reduction chain is the critical path (exchange done at 8 of 12.5 ms): top 25 % of
-        # the remote rows first, light 8 KB push ring — 12.5 ms vs 16.3 unstaged (hybrid 15.2, mixed
-        # per-rank structures 16-17: one global barrier per stage makes every rank wait for the
-        # largest request list of the stage).  N=8: the exchange is the critical path (done at 6.6
-        # of 7.7 ms): a smaller first group (15 %) so stage 1 starts when the 1 ms own-source stage
-        # ends, and the 16 KB ring (more bytes in flight under HBM contention): 7.70 ms vs 8.22 with
-        # 8 KB, 8.77 with 25 %, 10.1 unstaged.
+        # (profiles/scaling/r2h_*, r3d_* ... r3m_*; per-rank timelines in the same files).  Every N
+        # splits by SOURCE and writes every output row at most TWICE: a 16-bit sum is rounded once
+        # per stage that touches the row, and the stated tolerance (1e-2 of sum|terms|) holds two
+        # bf16 roundings (2 * 2^-8), not three — three accumulating stages measured 1.06 of the bound.
+        #   N=2: own-source edges, then the remote ones; the own half hides the whole exchange.
+        #   N>=4: the own-source edges and the edges of the most-referenced remote rows in ONE
+        #   two-buffer launch (merge_own: gathers from x_local and from the receive buffer) after a
+        #   small first push, then the rest.  N=4: first group 3 % of the remote rows, 8 KB push ring:
+        #   13.5 ms (three accumulating stages: 12.7 ms but 3 roundings; unstaged 16.3).  N=8: 10 %,
+        #   16 KB ring (the exchange is the critical path there; more bytes in flight under HBM
+        #   contention): 7.68 ms (three stages 7.61; 8 KB ring 8.3; unstaged 10.1).
+        # Also measured and not used: hybrid / destination splits, per-rank mixed structures (one
+        # global barrier per stage makes every rank wait for the largest request list), larger push
+        # grids (296 CTAs slow the reduction more than they speed the exchange), L2 evict-first
+        # hints on the pushed rows (no effect).
         fracs = [float(v) for v in args.stage_fracs.split(",")] if args.stage_fracs else None
         if args.split == "auto":
             args.split = "source"
         if args.push_chunk < 0:
             args.push_chunk = 16384 if world >= 8 else 8192
+        if args.merge_own < 0:
+            args.merge_own = 1 if (world > 2 and args.split == "source") else 0
         if args.stages > 0:
             stages = args.stages
         elif args.split == "source":
             stages = 2 if world <= 2 else 3
             if fracs is None and stages == 3:
-                fracs = [0.15, 0.85] if world >= 8 else [0.25, 0.75]
+                if args.merge_own:
+                    fracs = [0.1, 0.9] if world >= 8 else [0.03, 0.97]
+                else:
+                    fracs = [0.15, 0.85] if world >= 8 else [0.25, 0.75]
         elif args.split == "hybrid":
             stages = 2 if world <= 2 else 3
         else:
@@ -496,7 +506,7 @@ def run_rmat(args):
         own = args.ownership if args.ownership != "auto" else ("xorfold" if world & (world - 1) == 0 else "cyclic")
         kw = dict(rank=rank, world=world, cyclic_rows=N, stages=stages, stage_fracs=fracs,
                   row_weight=args.row_weight, split=args.split, ownership=own, push_blocks=args.push_blocks,
-                  push_chunk=args.push_chunk)
+                  push_chunk=args.push_chunk, merge_own=bool(args.merge_own))
         try:
             agg = DistAggregator(bounds, src, dst, exchange=args.exchange, **kw)
             if args.exchange == "push":
@@ -623,6 +633,7 @@ def run_rmat(args):
               "exchange": args.exchange if world > 1 else None, "stages": stages if world > 1 else None,
               "stage_fracs": fracs if world > 1 else None,
               "split": args.split if world > 1 else None,
+              "merge_own": bool(args.merge_own) if world > 1 else None,
               "push_chunk": args.push_chunk if world > 1 else None, "push_blocks": args.push_blocks if world > 1 else None,
               "stage_edges_rank0": [p.E for p, *_ in plans] if world > 1 else None,
               "stage_recv_rows_rank0": ([agg.stage_row0[s + 1] - agg.stage_row0[s] for s in range(stages)]
@@ -1023,6 +1034,9 @@ def main():
                     help="rmat workloads at N>1: feature row i lives on rank i %% N (cyclic) or on the XOR of "
                          "the log2(N)-bit groups of i (xorfold: balanced on R-MAT ids, whose bits are skewed); "
                          "auto = xorfold for power-of-two N")
+    ap.add_argument("--merge-own", type=int, default=-1,
+                    help="rmat workloads at N>1, source split: reduce the own-source edges and the first remote "
+                         "group in one two-buffer launch (-1 = the measured best per N)")
     ap.add_argument("--push-chunk", type=int, default=-1,
                     help="rmat workloads at N>1: ring slot bytes of the TMA push (4096..16384; -1 = the measured "
                          "best per N: 8192 below 8 GPUs, 16384 at 8)")

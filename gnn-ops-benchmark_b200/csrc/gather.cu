@@ -157,6 +157,7 @@ struct PushTmaParams {
   int64_t start_chunk;            // rotation, so the ranks store to different receivers at any moment
   int rows_per_chunk;
   int chunk_bytes;                // ring slot size
+  int hint;                       // L2 evict_first on the rows read and stored (GNO_PUSH_HINT, default on)
 };
 
 __global__ void __launch_bounds__(32) push_rows_tma_kernel(const PushTmaParams p) {
@@ -173,6 +174,9 @@ __global__ void __launch_bounds__(32) push_rows_tma_kernel(const PushTmaParams p
   __syncwarp();
   const int64_t first = blockIdx.x, step = gridDim.x;
   const int64_t n_my = first < n_chunks ? (n_chunks - first + step - 1) / step : 0;
+  // rows are read once and stored once: keep them from displacing the hub rows the reduction
+  // running beside the push re-reads out of L2
+  const uint64_t pol = l2_policy_evict_first();
 
   auto locate = [&](int64_t it, int& q, int64_t& slot0, int& rows) {
     int64_t c = first + it * step + p.start_chunk;
@@ -197,7 +201,8 @@ __global__ void __launch_bounds__(32) push_rows_tma_kernel(const PushTmaParams p
       unsigned char* dst = buf + (size_t)st * p.chunk_bytes;
       for (int r = lane; r < rows; r += 32) {
         const int64_t row = p.b.serve_rows[slot0 + r];
-        bulk_g2s(dst + (size_t)r * rb, p.b.x + row * p.b.src_stride, rb, bar + st);
+        if (p.hint) bulk_g2s_hint(dst + (size_t)r * rb, p.b.x + row * p.b.src_stride, rb, bar + st, pol);
+        else bulk_g2s(dst + (size_t)r * rb, p.b.x + row * p.b.src_stride, rb, bar + st);
       }
     }
     const int64_t j = it - kTmaAhead;  // chunk whose rows have had two iterations to arrive
@@ -209,7 +214,8 @@ __global__ void __launch_bounds__(32) push_rows_tma_kernel(const PushTmaParams p
         int64_t slot0;
         locate(j, q, slot0, rows);
         char* out = p.b.peer_buf[q] + (p.b.row_off[q] + (slot0 - p.b.seg[q])) * p.b.dst_stride;
-        bulk_s2g(out, buf + (size_t)st * p.chunk_bytes, (uint32_t)rows * rb);
+        if (p.hint) bulk_s2g_hint(out, buf + (size_t)st * p.chunk_bytes, (uint32_t)rows * rb, pol);
+        else bulk_s2g(out, buf + (size_t)st * p.chunk_bytes, (uint32_t)rows * rb);
         bulk_commit();
       }
     }
@@ -386,6 +392,8 @@ int gno_push_rows(const void* x, int64_t row_bytes, int64_t src_stride_bytes, co
     PushTmaParams t;
     t.b = p;
     t.chunk_bytes = chunk_bytes;
+    static const int hint_env = getenv("GNO_PUSH_HINT") ? atoi(getenv("GNO_PUSH_HINT")) : 1;
+    t.hint = hint_env;
     t.rows_per_chunk = (int)(chunk_bytes / row_bytes);
     t.chunk0[0] = 0;
     for (int q = 0; q < n_peers; ++q)

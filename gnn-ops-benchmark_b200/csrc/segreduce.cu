@@ -46,6 +46,7 @@ struct SegParams {
   const int32_t* eid;
   const int32_t* erow;
   const void* x;
+  const void* x2;      // second gather base (gno_segment_reduce_two): gather ids >= x2_first read row id - x2_first of x2
   const void* w;
   void* out;
   int64_t* arg;
@@ -68,7 +69,15 @@ struct SegParams {
   int vec_out;    // out rows are aligned for VB-byte vector stores and F*s is a multiple of VB
   int tma_ok;     // edge-record arrays are 16-byte aligned (bulk copies allowed)
   int staged;     // use the TMA-staged kernel (record slab of a CTA fits the shared-memory budget)
+  unsigned x2_first;  // 0xffffffff when there is no second base (no gather id reaches it)
 };
+
+// Address of row `idx` of the gather source: two bases, one compare and a select (xcol2 is
+// pre-offset by -x2_first rows, so both forms add idx * ldx).
+__device__ __forceinline__ const char* gather_addr(const char* xcol, const char* xcol2, unsigned x2_first,
+                                                   unsigned idx, unsigned ldx) {
+  return (idx >= x2_first ? xcol2 : xcol) + (uint64_t)idx * ldx;
+}
 
 template <int VB>
 struct Words {
@@ -384,6 +393,8 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
   const bool vact = active && (v < p.nvec);
   const char* xcol = static_cast<const char*>(p.x) + (int64_t)v * VB;
   const unsigned ldx = (unsigned)p.ldx_bytes;
+  const unsigned x2f = p.x2_first;
+  const char* xcol2 = p.x2 ? static_cast<const char*>(p.x2) - (int64_t)x2f * ldx + (int64_t)v * VB : xcol;
   const bool stream_idx = (p.ncoltiles == 1);
   const uint64_t pol_stream = l2_policy_evict_first();
   const int32_t* erow = p.erow + k0;
@@ -443,7 +454,7 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
         const int idx = __shfl_sync(0xffffffffu, my_idx, lane0 + u);
         if constexpr (ARG) e_u[u] = __shfl_sync(0xffffffffu, my_e, lane0 + u);
         if constexpr (HAS_W) w_u[u] = __shfl_sync(0xffffffffu, my_w, lane0 + u);
-        if (vact) val[u] = ld_vec<VB>(xcol + (uint64_t)((unsigned)idx) * ldx);
+        if (vact) val[u] = ld_vec<VB>(gather_addr(xcol, xcol2, x2f, (unsigned)idx, ldx));
       }
       // rows ascend: the batch's last row equal to cur_row means no boundary inside it
       const int row_last = __shfl_sync(0xffffffffu, my_row, lane0 + U - 1);
@@ -497,7 +508,7 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
       if constexpr (HAS_W) w1 = __shfl_sync(0xffffffffu, my_w, src_lane);
       if (slot < rem) {
         Words<VB> val1;
-        if (vact) val1 = ld_vec<VB>(xcol + (uint64_t)((unsigned)idx) * ldx);
+        if (vact) val1 = ld_vec<VB>(gather_addr(xcol, xcol2, x2f, (unsigned)idx, ldx));
         if (row_u != cur_row) {
           const int kk = t + slot;
           if (vact)
@@ -592,6 +603,8 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
   if (!vact) return;  // no warp-synchronous code below: idle lanes simply leave
   const char* xcol = static_cast<const char*>(p.x) + (int64_t)v * VB;
   const unsigned ldx = (unsigned)p.ldx_bytes;
+  const unsigned x2f = p.x2_first;
+  const char* xcol2 = p.x2 ? static_cast<const char*>(p.x2) - (int64_t)x2f * ldx + (int64_t)v * VB : xcol;
   const int* rowp = s_row + soff;
   const int* idxp = s_idx + soff;
   const int* ep = (sep_e ? s_e : s_idx) + soff;
@@ -628,7 +641,7 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int idx = has_idx ? idxp[t + u] : (int)(k0 + t + u);
-      val[u] = ld_vec<VB>(xcol + (uint64_t)((unsigned)idx) * ldx);
+      val[u] = ld_vec<VB>(gather_addr(xcol, xcol2, x2f, (unsigned)idx, ldx));
     }
     // rows ascend: the batch's last row equal to cur_row means no boundary inside it
     const bool simple = rowp[t + U - 1] == cur_row;
@@ -648,7 +661,7 @@ __global__ void __launch_bounds__(kSegThreads, (ARG || sizeof(T) == 2) ? kSegMin
 #pragma unroll 1
   for (; t < nv; ++t) {  // chunk tail
     const int idx = has_idx ? idxp[t] : (int)(k0 + t);
-    const Words<VB> val1 = ld_vec<VB>(xcol + (uint64_t)((unsigned)idx) * ldx);
+    const Words<VB> val1 = ld_vec<VB>(gather_addr(xcol, xcol2, x2f, (unsigned)idx, ldx));
     const int row_u = rowp[t];
     if (row_u != cur_row) close_row(row_u, t);
     int e1 = 0;
@@ -955,7 +968,17 @@ int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows, int64_t 
                        void* out, int64_t ldo, int64_t* arg, int64_t arg_fill, int64_t F, int dtype,
                        int reduce, int accumulate, void* wsp, size_t ws_bytes,
                        gno_stream_t stream) {
+  return gno_segment_reduce_two(g, x, x_rows, ldx, nullptr, 0, w, out, ldo, arg, arg_fill, F, dtype, reduce,
+                                accumulate, wsp, ws_bytes, stream);
+}
+
+int gno_segment_reduce_two(const gno_csr* g, const void* x, int64_t x_rows, int64_t ldx, const void* x2,
+                           int64_t x2_rows, const void* w, void* out, int64_t ldo, int64_t* arg,
+                           int64_t arg_fill, int64_t F, int dtype, int reduce, int accumulate, void* wsp,
+                           size_t ws_bytes, gno_stream_t stream) {
   cudaStream_t s = (cudaStream_t)stream;
+  GNO_CHECK_ARG(x2 == nullptr || (x2_rows >= 0 && x_rows + x2_rows < (int64_t(1) << 31)),
+                "gno_segment_reduce_two: x_rows + x2_rows must stay below 2^31");
   GNO_CHECK_ARG(g != nullptr, "gno_segment_reduce: graph is NULL");
   GNO_CHECK_ARG(dtype == GNO_F32 || dtype == GNO_F16 || dtype == GNO_BF16,
                 "gno_segment_reduce: unknown dtype %d", dtype);
@@ -979,13 +1002,13 @@ int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows, int64_t 
     return fail(GNO_ERR_UNSUPPORTED, "gno_segment_reduce: edge weights with MUL are not defined upstream");
 
   const int es = dtype_size(dtype);
-  GNO_CHECK_ARG((((uintptr_t)x | (uintptr_t)out) % es) == 0,
+  GNO_CHECK_ARG((((uintptr_t)x | (uintptr_t)x2 | (uintptr_t)out) % es) == 0,
                 "gno_segment_reduce: buffers not aligned to the element size");
   // Widest gather vector the row starts of x allow.  A row whose length is not a multiple of it
   // is still read with full vectors when the row stride leaves room for the over-read (x padded
   // by the caller, e.g. F=602: 1204-byte bf16 rows stored with a 1216-byte stride); the extra
   // columns are dropped on output.
-  const uintptr_t ax = (uintptr_t)x | (uintptr_t)(ldx * es);
+  const uintptr_t ax = (uintptr_t)x | (uintptr_t)x2 | (uintptr_t)(ldx * es);
   int vb = 16;
   while (vb > es && (ax % vb) != 0) vb >>= 1;
   while (vb > es && (F * es) % vb != 0 && ceil_div(F * es, vb) * vb > ldx * es) vb >>= 1;
@@ -996,6 +1019,8 @@ int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows, int64_t 
   p.eid = g->eid;
   p.erow = g->erow;
   p.x = x;
+  p.x2 = x2;
+  p.x2_first = x2 ? (unsigned)x_rows : 0xffffffffu;
   p.w = w;
   p.out = out;
   p.arg = arg;

@@ -64,6 +64,9 @@ PROTOTYPES = {
     "gno_segment_reduce": (c_int, [POINTER(gno_csr), c_void_p, c_int64, c_int64, c_void_p,
                                    c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int,
                                    c_int, c_void_p, c_size_t, c_void_p]),
+    "gno_segment_reduce_two": (c_int, [POINTER(gno_csr), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p,
+                                       c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int,
+                                       c_int, c_void_p, c_size_t, c_void_p]),
     "gno_segment_reduce_int": (c_int, [POINTER(gno_csr), c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                        c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "gno_segment_reduce_lastdim": (c_int, [POINTER(gno_csr), c_void_p, c_int64, c_int64, c_int64,

@@ -107,7 +107,8 @@ class DistAggregator:
 
     def __init__(self, bounds, src_global, dst_local, rank=None, world=None, group=None, stages=1,
                  feature_bounds=None, exchange="allgather", cyclic_rows=None, stage_fracs=None,
-                 row_weight=0, split="dest", ownership="cyclic", push_blocks=148, push_chunk=0):
+                 row_weight=0, split="dest", ownership="cyclic", push_blocks=148, push_chunk=0,
+                 merge_own=False):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -163,6 +164,12 @@ class DistAggregator:
             if split not in ("dest", "source", "hybrid"):
                 raise ValueError("split must be 'dest', 'source', 'hybrid' or 'mixed[min_degree]'")
             self.split = split if self.xstages > 1 else "dest"
+            # merge_own (source split): the own-source edges and the edges of the first remote group
+            # are reduced in ONE launch that gathers from two buffers (x_local and the receive
+            # buffer, gno_segment_reduce_two) — one pass over the output and one rounding of a
+            # 16-bit sum fewer than reducing them as two accumulating stages, at the price of
+            # waiting for the first (small) push before any reduction starts.
+            self.merge_own = bool(merge_own) and self.split == "source" and self.xstages > 2
         self.stages = max(1, min(int(stages), max(self.max_rows, 1)))
         # single-stage layout: row of the padded gather buffer [P * max_rows, F]
         self.src_padded = owner * self.max_rows + local if exchange in ("allgather", "allgather_push") else None
@@ -492,7 +499,7 @@ class DistAggregator:
 
     def xstage_plans(self):
         """needed / push exchange with K stages: one plan per stage
-        [(plan, gidx, eid, row_lo, row_hi, accumulate)].  split="dest": the plan of destination
+        [(plan, gidx, eid, row_lo, row_hi, accumulate, two_buffers)].  split="dest": the plan of destination
         sub-range [row_lo, row_hi); split="source": a plan over all rows holding the edges whose
         source lies in group s, accumulated onto the earlier stages.  eid maps a sorted edge back
         to its position in this rank's edge list (the arg outputs)."""
@@ -502,7 +509,16 @@ class DistAggregator:
             for s in range(self.xstages):
                 if self.xstages == 1:
                     p, gidx = self.plan()
-                    self._stage_plans.append((p, gidx, p.perm, 0, self.n_out, False))
+                    self._stage_plans.append((p, gidx, p.perm, 0, self.n_out, False, False))
+                    continue
+                if self.merge_own and s == 0:
+                    continue            # reduced together with stage 1
+                if self.merge_own and s == 1:
+                    where = torch.nonzero(self.stage_of_edge <= 1).flatten()
+                    p = planmod.build_plan(self.dst_local[where], self.n_out)
+                    own_e = self.stage_of_edge[where] == 0
+                    ids = torch.where(own_e, self.src_local[where], self.src_needed[where] + self.n_local)
+                    self._stage_plans.append((p, p.sorted_ids(ids), p.sorted_ids(where), 0, self.n_out, False, True))
                     continue
                 where = torch.nonzero(self.stage_of_edge == s).flatten()
                 if self.split == "source" or (self.split == "hybrid" and s == 0):
@@ -515,7 +531,7 @@ class DistAggregator:
                 own = self.split in ("source", "hybrid") and s == 0   # rows of x_local, not of the receive buffer
                 gidx = p.sorted_ids((self.src_local if own else self.src_needed)[where])
                 eid = p.sorted_ids(where)
-                self._stage_plans.append((p, gidx, eid, lo, hi, acc))
+                self._stage_plans.append((p, gidx, eid, lo, hi, acc, False))
         return self._stage_plans
 
     def reduce_stages(self, recv, reduce, out, want_arg=False, arg=None, events=None, x_local=None):
@@ -527,14 +543,18 @@ class DistAggregator:
         own0 = self.split in ("source", "hybrid") and self.xstages > 1
         if own0 and x_local is None:
             raise ValueError("split='source' reduces stage 0 from x_local")
-        for s, (p, gidx, eid, lo, hi, acc) in enumerate(self.xstage_plans()):
+        plans = self.xstage_plans()
+        first = self.xstages - len(plans)     # merge_own: the list starts at exchange stage 1
+        for k, (p, gidx, eid, lo, hi, acc, dual) in enumerate(plans):
+            s = k + first
             if events is not None and not (own0 and s == 0):
                 cur.wait_event(events[s])
             self._mark(f"reduce{s} start", cur)
             if hi == lo or (acc and p.E_valid == 0):
                 continue
-            r = ops.segment_reduce(p, x_local if (own0 and s == 0) else recv, reduce, gidx=gidx, eid=eid,
-                                   want_arg=want_arg,
+            own_rows = (own0 and s == 0) or dual
+            r = ops.segment_reduce(p, x_local if own_rows else recv, reduce, gidx=gidx, eid=eid,
+                                   want_arg=want_arg, x2=recv if dual else None,
                                    arg_fill=self.dst_local.numel(), out=out[lo:hi], accumulate=acc)
             if want_arg:
                 arg[lo:hi].copy_(r[1])

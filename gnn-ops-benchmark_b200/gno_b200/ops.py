@@ -78,12 +78,14 @@ def clear_caches():
 
 # ------------------------------------------------------------ segment reduce --
 def segment_reduce(plan, x, reduce, *, gidx=None, eid=None, weights=None, out=None,
-                   accumulate=False, want_arg=False, arg_fill=None):
+                   accumulate=False, want_arg=False, arg_fill=None, x2=None):
     """out[i, :] = reduce_{k in row i} weights[k] * x[gidx[k], :]   (x is 2-D).
 
     gidx/eid: int32 [E] tensors or None (identity).  Returns out or (out, arg).
+    x2: second gather buffer (same dtype, width and row stride as x): ids >= x.size(0) read row
+    id - x.size(0) of x2 (gno_segment_reduce_two).
     """
-    _need_cuda(x, gidx, eid, weights, out)
+    _need_cuda(x, gidx, eid, weights, out, x2)
     if x.dim() != 2:
         raise ValueError("segment_reduce expects a 2-D x")
     if x.stride(1) != 1 and x.size(1) > 1:
@@ -104,7 +106,12 @@ def segment_reduce(plan, x, reduce, *, gidx=None, eid=None, weights=None, out=No
         arg_fill = plan.E
     if weights is not None:
         weights = weights.to(x.dtype).contiguous()
-    x = _pad_for_gather(x, plan)
+    if x2 is not None:
+        if x2.dtype != x.dtype or x2.dim() != 2 or x2.size(1) != F or not x.is_contiguous() or \
+                not x2.is_contiguous() or (F * x.element_size()) % 16:
+            raise ValueError("segment_reduce: x2 must match x (dtype, width), both contiguous with 16-byte rows")
+    else:
+        x = _pad_for_gather(x, plan)
     csr = plan.csr(gidx, eid if want_arg else None)
     nbytes = ctypes.c_size_t()
     check(lib.gno_segment_reduce_workspace(ctypes.byref(csr), F, dt, red, 1 if want_arg else 0,
@@ -113,9 +120,10 @@ def segment_reduce(plan, x, reduce, *, gidx=None, eid=None, weights=None, out=No
     ldx = x.stride(0) if x.size(0) > 1 else max(F, 1)
     ldo = out.stride(0) if N > 1 else max(F, 1)
     with _on_device(dev):
-        check(lib.gno_segment_reduce(ctypes.byref(csr), _ptr(x), x.size(0), ldx, _ptr(weights),
-                                     _ptr(out), ldo, _ptr(arg), int(arg_fill), F, dt, red,
-                                     1 if accumulate else 0, _ptr(ws), nbytes.value, _stream(dev)))
+        check(lib.gno_segment_reduce_two(ctypes.byref(csr), _ptr(x), x.size(0), ldx, _ptr(x2),
+                                         x2.size(0) if x2 is not None else 0, _ptr(weights),
+                                         _ptr(out), ldo, _ptr(arg), int(arg_fill), F, dt, red,
+                                         1 if accumulate else 0, _ptr(ws), nbytes.value, _stream(dev)))
     return (out, arg) if want_arg else out
 
 

@@ -190,6 +190,21 @@ int gno_segment_reduce(const gno_csr* g, const void* x, int64_t x_rows,
                        gno_stream_t stream);
 
 /*
+ * The same reduction with the gather source in TWO buffers of the same row
+ * stride and dtype: gather ids below x_rows read x, ids x_rows + j read row j
+ * of x2 (j < x2_rows).  The partitioned aggregation uses it to reduce the
+ * edges whose source row the rank owns (its own feature shard) and the edges
+ * whose source arrived over NVLink (the receive buffer) in ONE pass over the
+ * output instead of two accumulating ones (new work, no reference
+ * counterpart: the reference is single-GPU).
+ */
+int gno_segment_reduce_two(const gno_csr* g, const void* x, int64_t x_rows, int64_t ldx,
+                           const void* x2, int64_t x2_rows, const void* w, void* out,
+                           int64_t ldo, int64_t* arg, int64_t arg_fill, int64_t F,
+                           int dtype, int reduce, int accumulate, void* ws,
+                           size_t ws_bytes, gno_stream_t stream);
+
+/*
  * Integer form (int32 / int64 values, exact int64 accumulation): torch_scatter.scatter on
  * integer tensors — PyG's TopKPooling / to_dense_batch count nodes per graph with
  * scatter_add(batch.new_ones(n), batch, dim=0) (graph_benchmark/models/ptg_models.py:165-172).

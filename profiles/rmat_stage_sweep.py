@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--row-weight", type=int, default=4)
     ap.add_argument("--settings", default="push:1;push:2::source;push:3:0.1,0.9:source;push:4:0.05,0.25,0.7:source",
-                    help="';'-separated exchange:stages[:fracs[:split[:ownership[:push_blocks]]]]")
+                    help="';'-separated exchange:stages[:fracs[:split[:ownership[:push_blocks[:merge_own[:push_chunk]]]]]]")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -78,12 +78,14 @@ def main():
         split = parts[3] if len(parts) > 3 and parts[3] else "dest"
         own = parts[4] if len(parts) > 4 and parts[4] else "cyclic"
         pblocks = int(parts[5]) if len(parts) > 5 and parts[5] else 148
+        merge = bool(int(parts[6])) if len(parts) > 6 and parts[6] else False
+        chunk = int(parts[7]) if len(parts) > 7 and parts[7] else 0
         gno_b200.clear_caches()
         torch.cuda.empty_cache()
         t0 = time.perf_counter()
         agg = DistAggregator(bounds, src, dst, rank=rank, world=world, cyclic_rows=N, exchange=mode, stages=K,
                              stage_fracs=fracs, row_weight=args.row_weight, split=split, ownership=own,
-                             push_blocks=pblocks)
+                             push_blocks=pblocks, merge_own=merge, push_chunk=chunk)
         plans = agg.xstage_plans()
         if mode == "push":
             recv = agg._push_buffer(F, dtype, dev)[0][:agg.n_needed]
@@ -119,7 +121,7 @@ def main():
         mx = info.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(json.dumps({"workload": args.workload, "n_gpus": world, "exchange": mode, "stages": K, "split": split, "ownership": own, "push_blocks": pblocks,
+            print(json.dumps({"workload": args.workload, "n_gpus": world, "exchange": mode, "stages": K, "split": split, "ownership": own, "push_blocks": pblocks, "merge_own": merge, "push_chunk": chunk,
                               "stage_fracs": fracs, "stage_edges_rank0": [p.E for p, *_ in plans], "step_ms": round(step_ms, 3),
                               "exchange_only_ms": round(xonly, 3), "reduce_only_ms": round(ronly, 3),
                               "reduce_only_ms_per_rank": ronly_ranks,

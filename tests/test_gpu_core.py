@@ -156,6 +156,31 @@ def test_gather_scatter_split_rows(cuda, dtype, reduce, E, N, F, split):
         close(r, want, dtype, scale)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("reduce", ["sum", "max"])
+def test_two_buffer_gather(cuda, dtype, reduce):
+    """gno_segment_reduce_two: gather ids below x.size(0) read x, the rest read x2 — bit-identical
+    to one launch over the concatenated buffer (same plan, same order of additions)."""
+    import gno_b200
+    from gno_b200 import plan as planmod
+    g = torch.Generator().manual_seed(11)
+    N, E, F, R = 700, 90_000, 128, 5000
+    dst = (torch.rand(E, generator=g) ** 3 * N).long().clamp_(0, N - 1)
+    src = torch.randint(0, R, (E,), generator=g)
+    x = ((torch.randn(R, F, generator=g) * 4).round() / 4).to(dtype).to(cuda)
+    plan = planmod.build_plan(dst.to(cuda), N)
+    gidx = plan.sorted_ids(src.to(cuda))
+    arg = reduce == "max"
+    whole = gno_b200.segment_reduce(plan, x, reduce, gidx=gidx, eid=plan.perm, want_arg=arg)
+    for cut in (1, 1234, R - 1):
+        a, b = x[:cut].contiguous(), x[cut:].contiguous()
+        two = gno_b200.segment_reduce(plan, a, reduce, gidx=gidx, eid=plan.perm, want_arg=arg, x2=b)
+        if arg:
+            assert torch.equal(two[0], whole[0]) and torch.equal(two[1], whole[1])
+        else:
+            assert torch.equal(two, whole)
+
+
 def test_empty_rows_and_sentinels(cuda):
     import gno_b200
     src = torch.tensor([[1.0, -2.0], [3.0, 0.5]])

@@ -107,6 +107,14 @@ def _worker(rank, world, port, ret):
         xl = xp[xorfold_global_ids(rank, world, xp.size(0) // world)].contiguous().to(dev)
         for _ in range(3):
             ok &= torch.allclose(aggx.aggregate(xl, "sum").cpu(), wsum[lo:hi], rtol=1e-5, atol=1e-3)
+        # merge_own: own-source edges and the first remote group in one two-buffer launch
+        for K, fr in ((3, [0.3, 0.7]), (4, [0.2, 0.3, 0.5])):
+            aggm = DistAggregator(bounds, shards[rank][0].to(dev), shards[rank][1].to(dev), exchange="push",
+                                  cyclic_rows=xp.size(0), ownership="xorfold", stages=K, stage_fracs=fr,
+                                  split="source", merge_own=True)
+            for _ in range(3):
+                ok &= torch.allclose(aggm.aggregate(xl, "sum").cpu(), wsum[lo:hi], rtol=1e-5, atol=1e-3)
+                ok &= torch.allclose(aggm.aggregate(xl, "mean").cpu(), wmean[lo:hi], rtol=1e-5, atol=1e-3)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
@@ -157,6 +165,10 @@ def _worker_world1(rank, world, port, ret):
                                  stages=3, stage_fracs=[0.1, 0.9], split=split)
             for _ in range(2):
                 ok &= torch.allclose(agg.aggregate(x.to(dev), "sum").float().cpu(), wsum, rtol=1e-2, atol=1e-2)
+        agg = DistAggregator(bounds, src.to(dev), dst.to(dev), rank=0, world=1, exchange="push", cyclic_rows=N,
+                             stages=3, stage_fracs=[0.1, 0.9], split="source", merge_own=True)
+        for _ in range(2):
+            ok &= torch.allclose(agg.aggregate(x.to(dev), "sum").float().cpu(), wsum, rtol=1e-2, atol=1e-2)
         ret[0] = bool(ok)
     finally:
         dist.destroy_process_group()
