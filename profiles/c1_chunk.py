@@ -1,3 +1,5 @@
+"""C1-shaped scatter_sum (F=64 fp32, L2 flushed) at three sizes over the chunk length of the plan
+(GNO_SEG_PDL=0 disables the programmatic dependent launch of the finish kernel)."""
 import os, sys, statistics
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gnn-ops-benchmark_b200"))
@@ -10,7 +12,7 @@ for (E, N, F) in ((1_000_000, 100_000, 64), (4_000_000, 400_000, 64), (250_000, 
     src = torch.rand(E, F, device=dev, generator=g)
     idx = torch.randint(0, N, (E,), device=dev, generator=g)
     out = torch.empty(N, F, device=dev)
-    for cl in (32, 64, 128, 256):
+    for cl in (32, 64, 96, 128, 160, 192, 256):
         plan = planmod.build_plan(idx, N, chunk_len=cl)
         ts = []
         for _ in range(15):
