@@ -472,10 +472,13 @@ def run_rmat(args):
         #   N=2: own-source edges, then the remote ones; the own half hides the whole exchange.
         #   N>=4: the own-source edges and the edges of the most-referenced remote rows in ONE
         #   two-buffer launch (merge_own: gathers from x_local and from the receive buffer) after a
-        #   small first push, then the rest.  N=4: first group 3 % of the remote rows, 8 KB push ring:
-        #   13.5 ms (three accumulating stages: 12.7 ms but 3 roundings; unstaged 16.3).  N=8: 10 %,
-        #   16 KB ring (the exchange is the critical path there; more bytes in flight under HBM
-        #   contention): 7.68 ms (three stages 7.61; 8 KB ring 8.3; unstaged 10.1).
+        #   small first push, then the rest.  The first group is sized so that the merged launch ends
+        #   when the exchange does: reduction work done beside the push is slow, work left for the
+        #   last stage waits for the exchange.  N=4: the top 0.8 % of the remote rows (they carry 44 %
+        #   of the remote edges), 8 KB push ring: 12.75 ms (0.4 / 1.5 / 3 / 6 / 10 %: 13.0 / 13.0 /
+        #   13.3 / 14.2 / 15.0; three accumulating stages 12.7 but 3 roundings; unstaged 16.3).
+        #   N=8: 10 %, 16 KB ring (the exchange is the critical path there; more bytes in flight under
+        #   HBM contention): 7.44-7.68 ms (three stages 7.61; 8 KB ring 8.3; unstaged 10.1).
         # Also measured and not used: hybrid / destination splits, per-rank mixed structures (one
         # global barrier per stage makes every rank wait for the largest request list), larger push
         # grids (296 CTAs slow the reduction more than they speed the exchange), L2 evict-first
@@ -493,7 +496,7 @@ def run_rmat(args):
             stages = 2 if world <= 2 else 3
             if fracs is None and stages == 3:
                 if args.merge_own:
-                    fracs = [0.1, 0.9] if world >= 8 else [0.03, 0.97]
+                    fracs = [0.1, 0.9] if world >= 8 else [0.008, 0.992]
                 else:
                     fracs = [0.15, 0.85] if world >= 8 else [0.25, 0.75]
         elif args.split == "hybrid":
