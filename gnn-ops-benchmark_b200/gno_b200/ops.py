@@ -232,6 +232,10 @@ def scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum", return_ar
         raise IndexError("dim out of range")
     want_arg = return_arg and red in (GNO_MIN, GNO_MAX)
 
+    if 1 < index.dim() < src.dim():
+        # upstream's broadcast(index, src, dim): missing trailing dims are unsqueezed, then the
+        # index is expanded to src's shape (pytorch_scatter utils.py)
+        index = index.reshape(tuple(index.shape) + (1,) * (src.dim() - index.dim())).expand(src.shape)
     idx1d = _index_as_1d(index, src, dim)
     if idx1d is None:
         if index.dim() != src.dim():

@@ -581,6 +581,41 @@ def test_upstream_published_examples(cuda):
     assert torch.equal(out.cpu(), v["out"])
 
 
+def test_upstream_testsuite_tables(cuda):
+    """The `tests = [...]` tables of pytorch_scatter's own test suite (tests/golden/upstream_testsuite.py)
+    through the shim package: scatter_{sum,mul,mean,min,max} for every index shape class (1-D, 1-D
+    over rows, full-shape, fewer dims than src), segment_coo and segment_csr (shared and per-row
+    pointers).  Called twice so the cached-plan path of a full-shape index is covered too."""
+    import importlib.util
+    import os
+    import torch_scatter
+    spec = importlib.util.spec_from_file_location(
+        "upstream_testsuite", os.path.join(os.path.dirname(__file__), "golden", "upstream_testsuite.py"))
+    ut = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ut)
+    for v in ut.SCATTER:
+        src, index = v["src"].to(cuda), v["index"].to(cuda)
+        for _ in range(2):
+            assert torch.equal(torch_scatter.scatter_sum(src, index, v["dim"]).cpu(), v["sum"])
+            assert torch.equal(torch_scatter.scatter_add(src, index, v["dim"]).cpu(), v["sum"])
+            assert torch.equal(torch_scatter.scatter_mul(src, index, v["dim"]).cpu(), v["mul"])
+            assert torch.equal(torch_scatter.scatter_mean(src, index, v["dim"]).cpu(), v["mean"])
+            for red, fn in (("min", torch_scatter.scatter_min), ("max", torch_scatter.scatter_max)):
+                out, arg = fn(src, index, v["dim"])
+                assert torch.equal(out.cpu(), v[red]) and torch.equal(arg.cpu(), v["arg_" + red]), red
+                assert torch.equal(torch_scatter.scatter(src, index, v["dim"], reduce=red).cpu(), v[red])
+    for v in ut.SEGMENT:
+        src, index, indptr = v["src"].to(cuda), v["index"].to(cuda), v["indptr"].to(cuda)
+        for red in ("sum", "mean"):
+            assert torch.equal(torch_scatter.segment_coo(src, index, reduce=red).cpu(), v[red]), red
+            assert torch.equal(torch_scatter.segment_csr(src, indptr, reduce=red).cpu(), v[red]), red
+        for red in ("min", "max"):
+            out, arg = getattr(torch_scatter, f"segment_{red}_coo")(src, index)
+            assert torch.equal(out.cpu(), v[red]) and torch.equal(arg.cpu(), v["arg_" + red]), red
+            out, arg = getattr(torch_scatter, f"segment_{red}_csr")(src, indptr)
+            assert torch.equal(out.cpu(), v[red]) and torch.equal(arg.cpu(), v["arg_" + red]), red
+
+
 # ---- full-shape index: the one-launch shared-memory path and its edges --------------------------
 def _ref_minmax_with_out(m, a, out0, E, red):
     """torch_scatter's out= form for min/max from the oracle's fresh result: out0 is the starting

@@ -202,3 +202,43 @@ def test_oracle_matches_upstream_published_examples():
     assert torch.equal(i, v["out_index"]) and torch.equal(val, v["out_value"])
     v = up.SPMM
     assert torch.equal(oracle.spmm(v["index"], v["value"], v["m"], v["n"], v["matrix"]), v["out"])
+
+
+def _load_golden(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(os.path.dirname(__file__), "golden", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _upstream_broadcast(index, src):
+    """pytorch_scatter utils.broadcast for an index with fewer dims than src (trailing dims)."""
+    if 1 < index.dim() < src.dim():
+        index = index.reshape(tuple(index.shape) + (1,) * (src.dim() - index.dim())).expand(src.shape).contiguous()
+    return index
+
+
+def test_oracle_matches_upstream_testsuite_tables():
+    """The `tests = [...]` tables of upstream's own test suites (tests/golden/upstream_testsuite.py):
+    scatter sum / mul / mean / min / max + arg for every index shape class, and the segment tables
+    (segment_coo == scatter over the sorted index; segment_csr == the same after expanding indptr)."""
+    ut = _load_golden("upstream_testsuite")
+    for v in ut.SCATTER:
+        for red in ("sum", "mul", "mean", "min", "max"):
+            out, arg = oracle.scatter(v["src"], _upstream_broadcast(v["index"], v["src"]), v["dim"], None, red)
+            assert torch.equal(out, v[red]), (red, out)
+            if red in ("min", "max"):
+                assert torch.equal(arg, v["arg_" + red]), (red, arg)
+    for v in ut.SEGMENT:
+        dim = v["index"].dim() - 1
+        n_seg = v["indptr"].size(-1) - 1
+        # segment ids from the row pointers must reproduce the table's own index
+        ptr = v["indptr"].view(-1, n_seg + 1)
+        ids = torch.stack([torch.repeat_interleave(torch.arange(n_seg), p[1:] - p[:-1]) for p in ptr])
+        assert torch.equal(ids.view(v["index"].shape), v["index"])
+        for red in ("sum", "mean", "min", "max"):
+            out, arg = oracle.scatter(v["src"], v["index"], dim, n_seg, red)
+            assert torch.equal(out, v[red]), (red, out)
+            if red in ("min", "max"):
+                assert torch.equal(arg, v["arg_" + red]), (red, arg)
