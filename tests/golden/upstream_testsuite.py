@@ -9,8 +9,8 @@ What they pin beyond the README examples (tests/golden/upstream_published.py): s
 every shape class (1-D, 1-D index over a 2-D src along dim 0, full-shape 2-D index along dim 1, an
 index with FEWER dims than src that upstream broadcasts over the trailing dim), mul's identity 1
 and mean's / min's / max's 0 in an empty bucket, the arg sentinel = src.size(dim), arg = position
-along `dim`, and segment_coo / segment_csr (sorted index / row pointers, per-row pointers, an empty
-segment in the middle and at the end).  Upstream runs them with integer and floating dtypes; the
+along `dim`, and segment_coo / segment_csr / gather_coo / gather_csr (sorted index / row pointers, per-row
+pointers, an empty segment in the middle and at the end; test/test_gather.py).  Upstream runs them with integer and floating dtypes; the
 library's scatter covers floating values, so they are used as float32 here."""
 import torch
 
@@ -73,4 +73,16 @@ SEGMENT = [
          sum=T([[4., 21., 0., 11.], [12., 18., 12., 0.]]), mean=T([[2., 7., 0., 11.], [4., 9., 12., 0.]]),
          min=T([[1., 5., 0., 11.], [2., 8., 12., 0.]]), arg_min=T([[0, 2, 6, 5], [0, 3, 5, 6]]),
          max=T([[3., 9., 0., 11.], [6., 10., 12., 0.]]), arg_max=T([[1, 4, 6, 5], [2, 4, 5, 6]])),
+]
+
+# ---- test/test_gather.py (gather_coo over `index`, gather_csr over `indptr`) ---------------------
+# expected[..., e] = src[..., segment of e]; segment 2 is empty and segment 3 holds the last element
+GATHER = [
+    dict(src=T([1., 2., 3., 4.]), index=T([0, 0, 1, 1, 1, 3]), indptr=T([0, 2, 5, 5, 6]),
+         expected=T([1., 1., 2., 2., 2., 4.])),
+    dict(src=T([[1., 2.], [3., 4.], [5., 6.], [7., 8.]]), index=T([0, 0, 1, 1, 1, 3]), indptr=T([0, 2, 5, 5, 6]),
+         expected=T([[1., 2.], [1., 2.], [3., 4.], [3., 4.], [3., 4.], [7., 8.]])),
+    dict(src=T([[1., 3., 5., 7.], [2., 4., 6., 8.]]), index=T([[0, 0, 1, 1, 1, 3], [0, 0, 0, 1, 1, 2]]),
+         indptr=T([[0, 2, 5, 5, 6], [0, 3, 5, 6, 6]]),
+         expected=T([[1., 1., 3., 3., 3., 7.], [2., 2., 2., 4., 4., 6.]])),
 ]

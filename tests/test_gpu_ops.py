@@ -614,6 +614,10 @@ def test_upstream_testsuite_tables(cuda):
             assert torch.equal(out.cpu(), v[red]) and torch.equal(arg.cpu(), v["arg_" + red]), red
             out, arg = getattr(torch_scatter, f"segment_{red}_csr")(src, indptr)
             assert torch.equal(out.cpu(), v[red]) and torch.equal(arg.cpu(), v["arg_" + red]), red
+    for v in ut.GATHER:
+        src, index, indptr = v["src"].to(cuda), v["index"].to(cuda), v["indptr"].to(cuda)
+        assert torch.equal(torch_scatter.gather_coo(src, index).cpu(), v["expected"])
+        assert torch.equal(torch_scatter.gather_csr(src, indptr).cpu(), v["expected"])
 
 
 # ---- full-shape index: the one-launch shared-memory path and its edges --------------------------

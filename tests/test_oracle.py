@@ -242,3 +242,10 @@ def test_oracle_matches_upstream_testsuite_tables():
             assert torch.equal(out, v[red]), (red, out)
             if red in ("min", "max"):
                 assert torch.equal(arg, v["arg_" + red]), (red, arg)
+    for v in ut.GATHER:     # gather is pure indexing: the table against torch's own gather / index_select
+        idx, src = v["index"], v["src"]
+        if idx.dim() == 1:
+            got = src.index_select(0, idx)
+        else:
+            got = src.gather(idx.dim() - 1, idx)
+        assert torch.equal(got, v["expected"])
