@@ -393,6 +393,22 @@ def _scatter_chunked(src, idx1d, dim, out, N, reduce, red, want_arg, E):
 _FS_PLAN = os.environ.get("GNO_FS_PLAN", "1") != "0"
 
 
+def blocked_output_ids(idx3, N, kb):
+    """Blocked output id of every element of a full-shape index viewed as [B, E, K] — the sort key of
+    gno_scatter_planned's plan (include/gno_b200.h): ob = (((b*ncb + cb)*N + n) << kb) + kk with
+    k = cb*2^kb + kk, ncb = ceil(K / 2^kb); out-of-range destinations get `total` (they sort to the
+    tail and are dropped).  Returns (ids flattened in element order, total).  Device-agnostic."""
+    B, E, K = idx3.shape
+    dev = idx3.device
+    ncb = (K + (1 << kb) - 1) >> kb
+    total = (B * ncb * N) << kb
+    k = torch.arange(K, device=dev)
+    blk = (torch.arange(B, device=dev).view(B, 1, 1) * ncb + (k >> kb).view(1, 1, K)) * N   # (b*ncb + cb)*N
+    o = ((blk + idx3) << kb) + (k & ((1 << kb) - 1)).view(1, 1, K)
+    o = torch.where((idx3 >= 0) & (idx3 < N), o, torch.full_like(o, total)).reshape(-1)
+    return o, total
+
+
 def _full_shape_plan(index, dim, N, B, E, K, dt):
     """(order, ptr) of a full-shape index in the blocked layout of gno_scatter_planned
     (include/gno_b200.h), or None.  The first call on an index tensor takes the one-launch atomic
@@ -412,13 +428,7 @@ def _full_shape_plan(index, dim, N, B, E, K, dt):
 
     def build():
         dev = index.device
-        ncb = (K + (1 << kb) - 1) >> kb
-        total = (B * ncb * N) << kb
-        idx3 = index.view(B, E, K)
-        k = torch.arange(K, device=dev)
-        blk = (torch.arange(B, device=dev).view(B, 1, 1) * ncb + (k >> kb).view(1, 1, K)) * N   # (b*ncb + cb)*N
-        o = ((blk + idx3) << kb) + (k & ((1 << kb) - 1)).view(1, 1, K)
-        o = torch.where((idx3 >= 0) & (idx3 < N), o, torch.full_like(o, total)).reshape(-1)
+        o, total = blocked_output_ids(index.view(B, E, K), N, kb)
         iota = torch.arange(o.numel(), dtype=torch.int32, device=dev)
         skey, perm = sort_pairs(o, iota, 0, max(1, int(total).bit_length()))
         order = (torch.div(perm, K, rounding_mode="floor") % E).to(torch.int16 if order_bytes == 2 else torch.int32)

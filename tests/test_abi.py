@@ -185,3 +185,44 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only",
                         "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_planned_scatter_layout_restated_on_cpu():
+    """The blocked plan of gno_scatter_planned (include/gno_b200.h), built on the CPU from the same
+    host function the GPU path uses (ops.blocked_output_ids + a stable sort) and consumed by a
+    plain-Python restatement of the kernel's indexing, reproduces the oracle's scatter — so the
+    header's formula, the host builder and the kernel's addressing agree without a GPU."""
+    import numpy as np
+    import oracle
+    from gno_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    for (B, E, K, N, kb) in ((1, 23, 13, 9, 3), (2, 17, 5, 6, 2), (3, 11, 1, 4, 0), (1, 9, 20, 30, 4)):
+        src = ((torch.rand(B, E, K, generator=g) * 16).round() / 16 - 0.5)
+        idx = torch.randint(0, N, (B, E, K), generator=g)
+        idx.view(-1)[::7] = N + 2                       # out of range: dropped
+        o, total = ops.blocked_output_ids(idx, N, kb)
+        KB, ncb = 1 << kb, (K + (1 << kb) - 1) >> kb
+        assert total == B * ncb * N * KB
+        perm = torch.sort(o, stable=True).indices       # what gno_sort_pairs returns as payload
+        order = (torch.div(perm, K, rounding_mode="floor") % E)
+        ptr = torch.zeros(total + 1, dtype=torch.int64)
+        ptr[1:] = torch.cumsum(torch.bincount(o[o < total], minlength=total), 0)
+        out = torch.zeros(B, N, K)
+        arg = torch.full((B, N, K), E, dtype=torch.int64)
+        for blk in range(B * ncb):                       # one CTA per (b, column block)
+            b, cb = divmod(blk, ncb)
+            k0 = cb * KB
+            kw = min(KB, K - k0)
+            for i in range(N * KB):                      # blocked outputs of the CTA, in kernel order
+                n, kk = divmod(i, KB)
+                if kk >= kw:
+                    assert ptr[blk * N * KB + i] == ptr[blk * N * KB + i + 1]   # dead slots own nothing
+                    continue
+                seg = order[ptr[blk * N * KB + i]:ptr[blk * N * KB + i + 1]]
+                assert (seg[1:] > seg[:-1]).all()        # ascending e inside a segment (stable sort)
+                vals = src[b, seg, k0 + kk]
+                if seg.numel():
+                    out[b, n, k0 + kk] = vals.max()
+                    arg[b, n, k0 + kk] = seg[int(np.argmax(vals.numpy()))]
+        want, warg = oracle.scatter(src, idx, 1, N, "max")
+        assert torch.equal(out, want) and torch.equal(arg, warg)

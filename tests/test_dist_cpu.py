@@ -152,6 +152,30 @@ def _worker(rank, world, port, N, E, F, ret):
         recv = aggx.exchange_needed(xp[mine].contiguous(), gather_rows=lambda t, r: t.index_select(0, r))
         got, _ = oracle.gather_scatter(recv, aggx.src_needed, d_r, hi - lo, "sum")
         ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
+        # merge_own (source split): the own-source edges and the first remote group become ONE stage that
+        # gathers from two buffers — ids below n_local read x_local, the rest read the receive buffer
+        aggm = DistAggregator(bounds, s_r, d_r, exchange="needed", cyclic_rows=xp.size(0), ownership="xorfold",
+                              stages=3, stage_fracs=[0.3, 0.7], split="source", merge_own=True)
+        ok &= aggm.merge_own
+        x_loc = xp[mine].contiguous()
+        recv = aggm.exchange_needed(x_loc, gather_rows=lambda t, r: t.index_select(0, r))
+        both = torch.cat([x_loc, recv])                                  # what the two-base gather addresses
+        first = aggm.stage_of_edge <= 1
+        own_e = aggm.stage_of_edge[first] == 0
+        ids = torch.where(own_e, aggm.src_local[first], aggm.src_needed[first] + aggm.n_local)
+        ok &= bool((ids[own_e] < aggm.n_local).all()) and bool((ids[~own_e] >= aggm.n_local).all())
+        got = oracle.gather_scatter(both, ids, d_r[first], hi - lo, "sum")[0]
+        rest = ~first
+        got += oracle.gather_scatter(recv, aggm.src_needed[rest], d_r[rest], hi - lo, "sum")[0]
+        ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
+        # mixed<D>: the receiver picks its own structure from its average row degree
+        for thr, expect in ((1e9, "hybrid"), (0.0, "source")):
+            aggq = DistAggregator(bounds, s_r, d_r, exchange="needed", cyclic_rows=N, stages=3, stage_fracs=[0.4, 0.6],
+                                  split=f"mixed{thr:g}")
+            ok &= aggq.split == expect
+            recv = aggq.exchange_needed(x[rank::world].contiguous(), gather_rows=lambda t, r: t.index_select(0, r))
+            got, _ = oracle.gather_scatter(recv, aggq.src_needed, d_r, hi - lo, "sum")
+            ok &= torch.allclose(got, want[lo:hi], rtol=1e-5, atol=1e-4)
         ret[rank] = (bool(ok), int(d_r.numel()))
     finally:
         dist.destroy_process_group()
